@@ -1,0 +1,69 @@
+"""GPU parity against the reference's golden trajectories, through the C ABI (fleetrl_b200/libfleetstep.so).
+
+Same fixtures and the same tolerances as tests/test_oracle_golden.py:
+  bit-exact  : done, hours_left, target_soc, rainflow_length (cycle counts), soc, soc_deg, observation (float32)
+  rel 1e-12  : reward (device exp vs numpy exp in the two sigmoid penalties), cashflow (revenue factor regrouped)
+  abs 1e-13  : SOH, l ; rel 1e-12 : fd_cyc   (device pow/exp vs numpy, summation order of the stress terms)
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Golden, golden_names
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(g: Golden, **const_over):
+    from fleetrl_b200._lib import FleetStepHandle
+
+    consts = g.consts(**const_over)
+    h = FleetStepHandle(consts, g.tables, num_envs=1, device=0)
+    dev = h.device
+    keys = ["soc", "hours_left", "soc_deg", "soh", "target_soc", "rf_len", "fd_cyc", "life"]
+    out = {k: [] for k in ["obs", "reward", "cashflow", "done"] + keys}
+    obs = torch.zeros((1, h.D), dtype=torch.float32, device=dev)
+    rew = torch.zeros(1, dtype=torch.float32, device=dev)
+    done = torch.zeros(1, dtype=torch.uint8, device=dev)
+
+    def snap():
+        out["obs"].append(obs[0].cpu().numpy().copy())
+        for k in keys:
+            out[k].append(h.get(k)[0].cpu().numpy().copy())
+
+    step = 0
+    for ep, t0 in enumerate(g.start_idx):
+        h.reset(start_idx=torch.tensor([int(t0)], dtype=torch.int32, device=dev), obs=obs)
+        snap()
+        for k in range(g.n_steps_per_ep):
+            a = torch.from_numpy(g.actions[step][None, :].copy()).to(dev)
+            h.step(a, obs, rew, done)
+            step += 1
+            out["reward"].append(h.get("reward64")[0].item())
+            out["cashflow"].append(h.get("cashflow")[0].item())
+            out["done"].append(bool(done[0].item()))
+            snap()
+    assert h.check_errors() == 0
+    h.close()
+    return {k: np.array(v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_gpu_matches_reference(name):
+    g = Golden(name)
+    o = run_gpu(g)
+    r = g.traj
+    assert o["obs"].shape == r["obs"].shape
+    np.testing.assert_array_equal(o["done"], r["done"])
+    np.testing.assert_array_equal(o["hours_left"], r["hours_left"].astype(np.float32))
+    np.testing.assert_array_equal(o["target_soc"], r["target_soc"])
+    np.testing.assert_array_equal(o["soc"], r["soc"])
+    np.testing.assert_array_equal(o["soc_deg"], r["soc_deg"])
+    np.testing.assert_allclose(o["reward"], r["reward"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(o["cashflow"], r["cashflow"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(o["soh"], r["soh"], rtol=0, atol=1e-13)
+    if "rf_len" in r:
+        np.testing.assert_array_equal(o["rf_len"], r["rf_len"].astype(np.int32))
+        np.testing.assert_allclose(o["fd_cyc"], r["fd_cyc"], rtol=1e-12, atol=1e-18)
+        np.testing.assert_allclose(o["life"], r["life"], rtol=0, atol=1e-13)
+    np.testing.assert_array_equal(o["obs"], r["obs"])

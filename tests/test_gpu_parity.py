@@ -1,0 +1,101 @@
+"""GPU vs CPU-oracle parity on many envs with auto-reset, random starts and random actions (through the C ABI).
+
+Bit-exact (asserted with array_equal): done, time index, hours_left, soc, soc_deg, target flags, rainflow cycle
+counts / rainflow_length, observations (float32), terminal observations, start indices drawn by the device RNG.
+Tolerance: reward rel 1e-12 (exp), cashflow rel 1e-12 (regrouped revenue factor), SOH abs 1e-13, fd_cyc rel 1e-11.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import OracleFleet
+from synth_tables import make_consts, make_tables
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "lmd_7ev": dict(n_evs=7, days=12, use_case="lmd", E=96, steps=230),
+    "lmd_50ev": dict(n_evs=50, days=8, use_case="lmd", E=37, steps=120),
+    "ct_20ev_two_trips": dict(n_evs=20, days=10, use_case="ct", two_trips=True, E=64, steps=210, episode_hours=48),
+    "ut_1h_5ev": dict(n_evs=5, days=30, use_case="ut", sph=1, E=128, steps=110, episode_hours=48,
+                      over=dict(include_building=0, include_pv=0)),
+    "lmd_1ev": dict(n_evs=1, days=12, use_case="lmd", E=700, steps=110),
+    "lmd_300ev": dict(n_evs=300, days=6, use_case="lmd", E=3, steps=100),
+    "lmd_9ev_norm_nocarry": dict(n_evs=9, days=12, use_case="lmd", E=40, steps=200,
+                                 over=dict(normalize=1, carry_degradation_state=0)),
+    "lmd_6ev_linear_noaux": dict(n_evs=6, days=12, use_case="lmd", E=40, steps=200, over=dict(deg_mode=1, aux=0)),
+    "lmd_5ev_soh09": dict(n_evs=5, days=12, use_case="lmd", E=16, steps=120, over=dict(init_soh=0.9)),
+    "lmd_4ev_no_autoreset": dict(n_evs=4, days=12, use_case="lmd", E=8, steps=110, over=dict(auto_reset=0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gpu_vs_oracle(name):
+    from fleetrl_b200._lib import FleetStepHandle
+
+    cs = dict(CASES[name])
+    E, steps = cs.pop("E"), cs.pop("steps")
+    over = cs.pop("over", {})
+    use_case = cs.pop("use_case")
+    episode_hours = cs.pop("episode_hours", 24)
+    sph = cs.get("sph", 4)
+    cap0 = dict(lmd=60.0, ut=50.0, ct=16.7)[use_case]
+    tables, T = make_tables(seed=hash(name) % 1000, cap=cap0, **cs)
+    if not over.get("include_building", 1):
+        tables = dict(tables, load=None)
+    if not over.get("include_pv", 1):
+        tables = dict(tables, pv=None)
+    consts = make_consts(tables, T, cs["n_evs"], sph=sph, episode_hours=episode_hours, use_case=use_case, **over)
+    N = cs["n_evs"]
+
+    orc = OracleFleet(consts, tables, E, env_id_offset=1000)
+    gpu = FleetStepHandle(consts, tables, E, device=0, env_id_offset=1000)
+    dev = gpu.device
+    D = gpu.D
+    assert D == orc.D
+    rng = np.random.default_rng(7)
+
+    obs = torch.zeros((E, D), dtype=torch.float32, device=dev)
+    term = torch.full((E, D), -7.0, dtype=torch.float32, device=dev)
+    rew = torch.zeros(E, dtype=torch.float32, device=dev)
+    done = torch.zeros(E, dtype=torch.uint8, device=dev)
+
+    o_obs = orc.reset()                      # start indices from the counter RNG on both sides
+    gpu.reset(obs=obs)
+    np.testing.assert_array_equal(gpu.get("time_idx").cpu().numpy(), orc.get("time_idx"))
+    np.testing.assert_array_equal(obs.cpu().numpy(), o_obs)
+
+    exact = ["time_idx", "finish_idx", "hours_left", "soc", "soc_deg", "target_soc", "rf_len", "n_cycles", "ep_count"]
+    n_done = 0
+    for s in range(steps):
+        a = rng.uniform(-1, 1, (E, N)).astype(np.float32)
+        if s % 5 == 0:
+            a[rng.random((E, N)) < 0.3] = 0.0          # exact zeros: plateaus in the SOC history
+        if s % 7 == 0:
+            a[:] = 1.0                                  # everybody charges: overload penalties
+        o_obs, o_rew, o_cash, o_done, o_term = orc.step(a, want_terminal=True)
+        gpu.step(torch.from_numpy(a).to(dev), obs, rew, done, term)
+        g_done = done.cpu().numpy()
+        np.testing.assert_array_equal(g_done, o_done, err_msg=f"done step {s}")
+        for k in exact:
+            np.testing.assert_array_equal(gpu.get(k).cpu().numpy(), orc.get(k), err_msg=f"{k} step {s}")
+        np.testing.assert_allclose(gpu.get("reward64").cpu().numpy(), o_rew, rtol=1e-12, atol=1e-12, err_msg=f"reward step {s}")
+        np.testing.assert_allclose(gpu.get("cashflow").cpu().numpy(), o_cash, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(rew.cpu().numpy(), o_rew.astype(np.float32), rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(gpu.get("soh").cpu().numpy(), orc.get("soh"), rtol=0, atol=1e-13, err_msg=f"soh step {s}")
+        np.testing.assert_allclose(gpu.get("fd_cyc").cpu().numpy(), orc.get("fd_cyc"), rtol=1e-11, atol=1e-18)
+        np.testing.assert_allclose(gpu.get("life").cpu().numpy(), orc.get("life"), rtol=0, atol=1e-13)
+        np.testing.assert_allclose(gpu.get("overload").cpu().numpy(), orc.get("overload"), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(gpu.get("soc_viol").cpu().numpy(), orc.get("soc_viol"), rtol=1e-12, atol=1e-15)
+        np.testing.assert_array_equal(obs.cpu().numpy(), o_obs, err_msg=f"obs step {s}")
+        if consts.auto_reset and o_done.any():
+            idx = np.nonzero(o_done)[0]
+            np.testing.assert_array_equal(term.cpu().numpy()[idx], o_term[idx], err_msg=f"terminal obs step {s}")
+            n_done += len(idx)
+    if consts.auto_reset:
+        assert n_done > 0
+    g_stats, o_stats = gpu.stats(), orc.stats()
+    for k in o_stats:
+        np.testing.assert_allclose(g_stats[k], o_stats[k], rtol=1e-9, atol=1e-9, err_msg=f"stat {k}")
+    assert gpu.check_errors() == 0 and orc.err_flags() == 0
+    gpu.close()
