@@ -79,7 +79,7 @@ def make_tables(n_evs=7, days=12, sph=4, seed=0, two_trips=False, start_weekday=
 def make_consts(tables, T, n_evs, sph=4, episode_hours=24, use_case="lmd", **over):
     uc = dict(lmd=(11.0, 60.0, 60.0), ut=(22.0, 50.0, 50.0), ct=(4.6, 16.7, 16.7))[use_case]
     evse, lc_cap, cap0 = uc
-    max_load = float(tables["load"].max())
+    max_load = float(tables["load"].max()) if tables.get("load") is not None else 0.0
     grid = max(max_load * 1.1, max_load + 0.5 * n_evs * evse)
     if use_case == "ut" and n_evs > 1:
         grid = 1000.0
@@ -97,7 +97,7 @@ def make_consts(tables, T, n_evs, sph=4, episode_hours=24, use_case="lmd", **ove
         max_time_left=float(tables["time_left"].max()),
         min_price=(float(tables["delu"].min()) + 10.0) * 1.5, max_price=(float(tables["delu"].max()) + 10.0) * 1.5,
         min_tariff=float(tables["tariff"].min()) * 0.75, max_tariff=float(tables["tariff"].max()) * 0.75,
-        max_building=max_load, max_pv=float(tables["pv"].max()),
+        max_building=max_load, max_pv=float(tables["pv"].max()) if tables.get("pv") is not None else 0.0,
     )
     d.update(over)
     return FleetConsts.from_dict(d)
