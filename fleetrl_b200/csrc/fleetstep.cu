@@ -38,10 +38,11 @@
 namespace {
 
 constexpr int kThreads = 256;        // threads per CTA
+constexpr int kMinCtasPerSm = 4;     // register budget: 64 regs/thread -> 1024 resident threads per SM
 constexpr int kStatStripes = 64;     // atomic striping of the statistics vector
-constexpr int kNQ = 9;               // per-slot contributions: cost, rev, cr, dr, inv, oc, a*there, missing, dep
-enum { Q_COST = 0, Q_REV, Q_CR, Q_DR, Q_INV, Q_OC, Q_ATH, Q_MISS, Q_DEP };
-constexpr int kNSum = 8;             // quantities 0..7 are summed in phase 2; Q_DEP is chained onto the reward
+// per-slot contributions reduced per env (sequential, car order, one thread per (quantity, env))
+constexpr int kNQ = 5;
+enum { Q_REWARD = 0, Q_CASH, Q_ATH, Q_MISS, Q_NVIOL };
 
 // per-time flags
 constexpr uint32_t TF_TRIGGER = 1u;  // hour == 14 && minute == 45     fleet_environment.py:665
@@ -50,14 +51,17 @@ constexpr uint32_t TF_LUNCH = 2u;    // 11 < hour < 15                 fleet_env
 // per-env tile flags
 constexpr int EF_FROZEN = 1, EF_DONE = 2, EF_TRIGGER = 4, EF_LUNCH = 8, EF_RESET = 16;
 
-// One (time, vehicle) schedule record: SOC_on_return, time_left, There at this row, There at the previous row.
+// One (time, vehicle) schedule record, 32 bytes = one L2 sector: SOC_on_return, time_left, There at this row and
+// at the previous row, and the auxiliary observation terms of observer_bl_pv.py:85-91 for the un-raised target
+// SOC (pure functions of the schedule row, SURVEY B-4), already normalised when OracleNormalization is on.
 struct __align__(16) EvRec {
     double sr;
     float tl;
     uint8_t there, there_prev;
     uint16_t pad;
+    float tt, cl, hn, lax;   // target_soc*there, charging_left, hours_needed, laxity (float32 as observed)
 };
-static_assert(sizeof(EvRec) == 16, "EvRec must be 16 bytes");
+static_assert(sizeof(EvRec) == 32, "EvRec must be 32 bytes");
 
 // Everything EvCharger.charge / check_violation need that depends only on the time index t (host-precomputed).
 struct __align__(16) StepRow {
@@ -76,13 +80,17 @@ static_assert(sizeof(StepRow) == 64, "StepRow must be 64 bytes");
 struct StepParams {
     // sizes
     int E, N, T, R, L, D, Ha, Hb, hdr_stride, B;
+    unsigned long long RN;    // R * N
+    unsigned int n_magic;     // ceil(2^32 / N): j / N == __umulhi(j, n_magic) for j < 2^16
+    unsigned int h_magic;     // same for the header length Ha+Hb
+    int off_contrib, off_obs; // byte offsets of the contribution arrays / obs tile in dynamic shared memory
     // flags
-    int is_ct, calc_deg, deg_mode, carry, auto_reset, stack_u16;
+    int is_ct, calc_deg, deg_mode, carry, auto_reset, bulk_ok, eta_c_rcp_ok;
     int start_lo, start_hi;
     unsigned long long seed;
     long long env_id_offset;
     // constants
-    double dt, P, eta_c, eta_d, mult, cap0, target, target_lunch, eps, def_soc, min_lax;
+    double dt, P, eta_c, eta_c_rcp, eta_d, mult, cap0, target, target_lunch, eps, def_soc, min_lax;
     double pen_inv, pen_oc, clip_oc, pen_ovl, full_reward, evse, grid, init_soh, lc_batt_cap, hn_den, price_mult;
     double temperature, max_tl, max_soc, max_hn;
     float dt_f;
@@ -107,6 +115,12 @@ struct StepParams {
     double* stats;            // [kStatStripes][FLEET_S__COUNT]
     unsigned int* err_flags;  // [1]
     const int* next_start;    // [E] or nullptr
+    int2* wl;                 // [E] work list of the post kernel: {env, WL_* flags}
+    int* wl_count;            // [1]
+    unsigned int* wl_done;    // [1]
+    double* post_scratch_v;   // [grid_post][scratch_cap][64] fallback rainflow value ring
+    uint16_t* post_scratch_i; // [grid_post][scratch_cap][64]
+    int scratch_cap;          // power of two >= L+2
     // I/O
     const float* actions;
     float* obs;
@@ -124,9 +138,6 @@ struct EnvS {  // per-env scratch of a tile, shared memory
     int t, t_start, ep_count, flags;
     double S, F_cr, F_dr, Rfac, pv_share, gml, pvv;
     float* obs_dst;
-    double deg_sum;
-    int t0_new;
-    int pad;
 };
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
@@ -137,49 +148,61 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 }
 // Counter-based start-index draw keyed by (seed, global env id, episode number): integer work, bit-exact with
 // the oracle's draw_start.  Replaces the reference's unseeded random.choice (random_time_picker.py:31).
-__device__ __forceinline__ int draw_start(const StepParams& p, long long env_id, int episode_no) {
+__device__ __forceinline__ int draw_start(unsigned long long seed, int start_lo, int start_hi, long long env_id,
+                                          int episode_no) {
     unsigned long long h =
-        mix64(p.seed ^ mix64((unsigned long long)env_id * 0xD1B54A32D192ED03ull + (unsigned long long)(unsigned)episode_no));
-    unsigned long long span = (unsigned long long)(p.start_hi - p.start_lo) + 1ull;
-    return p.start_lo + (int)(h % span);
+        mix64(seed ^ mix64((unsigned long long)env_id * 0xD1B54A32D192ED03ull + (unsigned long long)(unsigned)episode_no));
+    unsigned long long span = (unsigned long long)(start_hi - start_lo) + 1ull;
+    return start_lo + (int)(h % span);
 }
 
 __device__ __forceinline__ EvRec load_rec(const EvRec* ptr) {
-    // one 128-bit read-only load
+    // two 128-bit read-only loads of one 32-byte sector (tables keep the default L2 policy; streaming state uses
+    // evict-first loads/stores so the tables stay resident)
     const int4 v = __ldg(reinterpret_cast<const int4*>(ptr));
+    const float4 w = __ldg(reinterpret_cast<const float4*>(ptr) + 1);
     EvRec r;
     r.sr = __hiloint2double(v.y, v.x);
     r.tl = __int_as_float(v.z);
     r.there = (uint8_t)(v.w & 0xff);
     r.there_prev = (uint8_t)((v.w >> 8) & 0xff);
     r.pad = 0;
+    r.tt = w.x; r.cl = w.y; r.hn = w.z; r.lax = w.w;
     return r;
 }
 
-// Per-EV part of Observer.get_obs + normalize_obs (observer_bl_pv.py:85-98, oracle_normalization.py:65-66,146-150):
-// simulated soc / hours_left, and the auxiliary block computed from the SCHEDULE columns of the row (SURVEY B-4).
+// Auxiliary observation terms for a vehicle whose target SOC was raised to 0.9 (rare; the table holds the values
+// for the configured target): observer_bl_pv.py:85-91, oracle_normalization.py:146-150.
+template <bool kNorm>
+__device__ __noinline__ float4 aux_on_the_fly(double tgt, double sr, float tl, int there, double lc_batt_cap, double hn_den,
+                                              double max_soc, double max_hn) {
+    const double th = (double)there;
+    double tt = tgt * th;
+    double cl = tt - sr;
+    double hn = cl * lc_batt_cap / hn_den;
+    double lax = ((double)tl / (hn + 0.001) - 1) * th;
+    lax = lax < 0 ? 0 : (lax > 5 ? 5 : lax);
+    if (kNorm) { tt = tt / max_soc; cl = cl / max_soc; hn = hn / max_hn; lax = lax / 5; }
+    return make_float4((float)tt, (float)cl, (float)hn, (float)lax);
+}
+
+// Per-EV part of the observation row `o` (global or shared memory): simulated soc / hours_left
+// (fleet_environment.py:645-649, oracle_normalization.py:65-66) and the auxiliary block.
 template <bool kNorm, bool kAux>
 __device__ __forceinline__ void write_ev_obs(const StepParams& p, float* __restrict__ o, int n, double soc, float hl,
-                                             const EvRec& rec, double tgt) {
+                                             const EvRec& rec, bool flip) {
     const int N = p.N;
     o[n] = (float)soc;
     o[N + n] = kNorm ? (float)((double)hl / p.max_tl) : hl;
     if (kAux) {
-        double th = (double)rec.there;
-        double tt = tgt * th;
-        double cl = tt - rec.sr;
-        double hn = cl * p.lc_batt_cap / p.hn_den;
-        double lax = ((double)rec.tl / (hn + 0.001) - 1) * th;
-        lax = lax < 0 ? 0 : (lax > 5 ? 5 : lax);
-        if (kNorm) {
-            tt = tt / p.max_soc; cl = cl / p.max_soc; hn = hn / p.max_hn; lax = lax / 5;
-        }
+        float4 ax = make_float4(rec.tt, rec.cl, rec.hn, rec.lax);
+        if (flip) ax = aux_on_the_fly<kNorm>(0.9, rec.sr, rec.tl, rec.there, p.lc_batt_cap, p.hn_den, p.max_soc, p.max_hn);
         float* a = o + 2 * N + p.Ha;
-        a[n] = (float)th;
-        a[N + n] = (float)tt;
-        a[2 * N + n] = (float)cl;
-        a[3 * N + n] = (float)hn;
-        a[4 * N + n] = (float)lax;
+        a[n] = (float)rec.there;
+        a[N + n] = ax.x;
+        a[2 * N + n] = ax.y;
+        a[3 * N + n] = ax.z;
+        a[4 * N + n] = ax.w;
     }
 }
 
@@ -221,137 +244,143 @@ __device__ __forceinline__ void reset_slot(const StepParams& p, int e, int n, in
     p.soh[i] = soh;
     p.hist[((size_t)e * p.R + 0) * p.N + n] = sdeg;
     if (obs_row) {
-        write_ev_obs<kNorm, kAux>(p, obs_row, n, soc, hl, rec, tgt);
+        write_ev_obs<kNorm, kAux>(p, obs_row, n, soc, hl, rec, flip);
         copy_hdr<kAux>(p, obs_row, n, t0);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ degradation
-// rainflow 3.2.0 extract_cycles (ASTM E1049-85 three-point method) streamed over one vehicle's SOC history with
-// an index stack in shared memory, feeding RainflowSeiDegradation.calculate_degradation
-// (rainflow_sei_degradation.py:128-206) without materialising the cycle list.
+// rainflow 3.2.0 extract_cycles (ASTM E1049-85 three-point method) over one vehicle's SOC history, feeding
+// RainflowSeiDegradation.calculate_degradation (rainflow_sei_degradation.py:128-206).
 //
-// The reference recomputes the full cycle list at every daily call and then takes the POSITIONAL slice
-// [rainflow_length-1 : len-1] (:146).  Streaming equivalent: cycles are numbered in generation order; cycle j
-// contributes to fd_cyc iff rf_len-1 <= j < m-1 where m is the final count, so the newest cycle is held back as
-// "pending" until the next one is emitted.  The mean over ALL cycles (:140) and max(End) = len-1 (:138) are
-// accumulated on the way.
-template <typename IdxT>
-struct RfStack {
-    IdxT* s;      // s[k * stride]
-    int stride;
-    __device__ __forceinline__ int get(int k) const { return (int)s[(size_t)k * stride]; }
-    __device__ __forceinline__ void set(int k, int v) { s[(size_t)k * stride] = (IdxT)v; }
+// Pass 1 (divergent by nature, kept lean): the reversal scan and the three-point stack.  The stack holds
+//   (sample index, value) pairs in a small shared-memory ring, the top three entries are mirrored in registers;
+//   every emitted cycle is recorded as one 32-bit word (i_a | i_b << 15 | full << 30) in shared memory and its
+//   mean is accumulated (the reference averages the means of ALL cycles, :140).
+// Pass 2 (convergent): the reference takes the POSITIONAL slice [rainflow_length-1 : len-1] of the full cycle list
+//   (:146); the recorded cycles a <= j < m-1 are replayed in list order and the SEI stress terms (pow/exp) are
+//   evaluated with all lanes of the warp active.
+// max(End) of the list is always len-1 (the provisional last reversal closes the last half cycle), :138.
+constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one work-list env per CTA)
+constexpr int kStackS = 32;   // shared-memory ring depth; deeper stacks fall back to a global-memory scratch ring
+
+struct RfRing {               // stack storage: entry k lives at [(k & mask) * stride]
+    double* v;
+    uint16_t* i;
+    int mask, stride;
 };
 
-struct SeiAcc {
-    int m;              // cycles emitted so far
-    int a;              // first selected list position (rf_len - 1)
-    double mean_sum;    // sum of cycle means, all cycles
-    double fsum;        // sum of stress over selected cycles
-    double max_dod;     // max range over selected cycles
-    bool have_pending;
-    double pend_eff, pend_mean, pend_range;
-    double s_temp;
-    bool stress;
-};
+struct RfOut { int m; double mean_sum; bool overflow; };
 
-__device__ __forceinline__ void sei_commit_pending(SeiAcc& acc) {
-    // pending is list position m-1 at the time of the call (before the new cycle is counted)
-    if (acc.have_pending && acc.stress && (acc.m - 1) >= acc.a) {
-        const double kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5, k_sigma = 1.04, sigma_ref = 0.5;
-        // (kd1 * dod**kd2 + kd3) ** -1 ; dod == 0 -> inf -> 0                  rainflow_sei_degradation.py:68
-        const double s_dod = 1.0 / (kd1 * pow(acc.pend_eff, kd2) + kd3);
-        const double s_soc = exp(k_sigma * (acc.pend_mean - sigma_ref));        // :70
-        acc.fsum += s_dod * s_soc * acc.s_temp;                                 // :77-79,174
-        if (acc.pend_range > acc.max_dod) acc.max_dod = acc.pend_range;
-    }
-}
+constexpr int kRfBatch = 16;  // history samples prefetched per batch (independent loads in flight per thread)
 
-__device__ __forceinline__ void sei_emit(SeiAcc& acc, double xa, double xb, double count) {
-    sei_commit_pending(acc);
-    const double range = fabs(xa - xb);
-    const double mean = 0.5 * (xa + xb);
-    double eff = range * count;                                                  // :170
-    eff = eff < 0 ? 0 : (eff > 1 ? 1 : eff);
-    acc.pend_eff = eff; acc.pend_mean = mean; acc.pend_range = range; acc.have_pending = true;
-    acc.mean_sum += mean;
-    acc.m++;
-}
+// kShared: ring in shared memory with compile-time geometry (mask kStackS-1, stride kPostThreads).
+// xs: per-thread staging of one prefetched batch, xs[u * kPostThreads] (shared memory).
+template <bool kShared>
+__device__ __forceinline__ RfOut rainflow_pass1(const double* __restrict__ x, int xstride, int len, RfRing rg,
+                                                uint32_t* __restrict__ recs, double* __restrict__ xs) {
+    RfOut out; out.m = 0; out.mean_sum = 0; out.overflow = false;
+    if (len < 2) return out;
+    int lo = 0, hi = 0, m = 0;
+    double mean_sum = 0;
+    double v1 = 0, v2 = 0, v3 = 0;     // values of the top three stack entries (v3 = top)
+    int i1 = 0, i2 = 0, i3 = 0;        // their sample indices
+    bool overflow = false;
+    const int mask = kShared ? (kStackS - 1) : rg.mask;
+    const int stride = kShared ? kPostThreads : rg.stride;
+    const int cap_ring = mask + 1;
 
-template <typename IdxT>
-__device__ __noinline__ void rainflow_stream(const double* __restrict__ x, int stride, int len, RfStack<IdxT> st,
-                                             SeiAcc& acc) {
-    if (len < 2) return;
-    int lo = 0, hi = 0;
-    double v1 = 0, v2 = 0, v3 = 0;  // values of the top three stack entries (v3 = top)
-#define XVAL(idx) (x[(size_t)(idx) * stride])
+#define RF_SLOT(k) (((k) & mask) * stride)
+#define RF_EMIT(ia, xa, ib, xb, full)                                                            \
+    do {                                                                                         \
+        mean_sum += 0.5 * ((xa) + (xb));                                                         \
+        recs[m * kPostThreads] = (uint32_t)(ia) | ((uint32_t)(ib) << 15) | ((uint32_t)(full) << 30);  \
+        m++;                                                                                     \
+    } while (0)
 #define RF_PUSH(idx, val)                                                                        \
     do {                                                                                         \
-        st.set(hi, (idx)); hi++;                                                                 \
-        v1 = v2; v2 = v3; v3 = (val);                                                            \
+        if (hi - lo >= cap_ring) { overflow = true; break; }                                     \
+        rg.v[RF_SLOT(hi)] = (val); rg.i[RF_SLOT(hi)] = (uint16_t)(idx); hi++;                    \
+        v1 = v2; i1 = i2; v2 = v3; i2 = i3; v3 = (val); i3 = (idx);                              \
         while (hi - lo >= 3) {                                                                   \
             const double X = fabs(v3 - v2), Y = fabs(v2 - v1);                                   \
             if (X < Y) break;                                                                    \
-            if (hi - lo == 3) { sei_emit(acc, v1, v2, 0.5); lo++; }                              \
+            if (hi - lo == 3) { RF_EMIT(i1, v1, i2, v2, 0); lo++; }                              \
             else {                                                                               \
-                sei_emit(acc, v1, v2, 1.0);                                                      \
-                st.set(hi - 3, st.get(hi - 1)); hi -= 2;                                         \
-                v2 = XVAL(st.get(hi - 2));                                                       \
-                if (hi - lo >= 3) v1 = XVAL(st.get(hi - 3));                                     \
+                RF_EMIT(i1, v1, i2, v2, 1);                                                      \
+                hi -= 2;                                                                         \
+                rg.v[RF_SLOT(hi - 1)] = v3; rg.i[RF_SLOT(hi - 1)] = (uint16_t)i3;                \
+                v2 = rg.v[RF_SLOT(hi - 2)]; i2 = rg.i[RF_SLOT(hi - 2)];                          \
+                if (hi - lo >= 3) { v1 = rg.v[RF_SLOT(hi - 3)]; i1 = rg.i[RF_SLOT(hi - 3)]; }    \
             }                                                                                    \
         }                                                                                        \
     } while (0)
 
-    double x_last = XVAL(0), xc = XVAL(1);
-    double d_last = xc - x_last;
-    RF_PUSH(0, x_last);
+    const double x0 = __ldcs(x), x1 = __ldcs(x + xstride);
+    double xc = x1, d_last = x1 - x0;
+    RF_PUSH(0, x0);
     int index = -1;
     double x_next = 0;
-    for (int pos = 2; pos < len; pos++) {
-        index = pos - 1;
-        x_next = XVAL(pos);
-        if (x_next == xc) continue;
-        const double d_next = x_next - xc;
-        if (d_last * d_next < 0) RF_PUSH(index, xc);
-        x_last = xc; xc = x_next; d_last = d_next;
+    for (int pos0 = 2; pos0 < len && !overflow; pos0 += kRfBatch) {
+        double xb[kRfBatch];
+#pragma unroll
+        for (int u = 0; u < kRfBatch; u++)
+            xb[u] = (pos0 + u < len) ? __ldcs(x + (size_t)(pos0 + u) * xstride) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kRfBatch; u++) xs[u * kPostThreads] = xb[u];
+        const int nbatch = min(kRfBatch, len - pos0);
+        for (int u = 0; u < nbatch && !overflow; u++) {
+            index = pos0 + u - 1;
+            x_next = xs[u * kPostThreads];
+            if (x_next != xc) {
+                const double d_next = x_next - xc;
+                if (d_last * d_next < 0) RF_PUSH(index, xc);
+                xc = x_next; d_last = d_next;
+            }
+        }
     }
-    if (index >= 0) RF_PUSH(index + 1, x_next);
-    while (hi - lo > 1) {
-        sei_emit(acc, XVAL(st.get(lo)), XVAL(st.get(lo + 1)), 0.5);
+    if (index >= 0 && !overflow) RF_PUSH(index + 1, x_next);
+    while (hi - lo > 1 && !overflow) {
+        const double xa = rg.v[RF_SLOT(lo)], xb2 = rg.v[RF_SLOT(lo + 1)];
+        const int ia = rg.i[RF_SLOT(lo)], ib = rg.i[RF_SLOT(lo + 1)];
+        RF_EMIT(ia, xa, ib, xb2, 0);
         lo++;
     }
 #undef RF_PUSH
-#undef XVAL
+#undef RF_EMIT
+#undef RF_SLOT
+    out.m = m; out.mean_sum = mean_sum; out.overflow = overflow;
+    return out;
 }
 
-// RainflowSeiDegradation.calculate_degradation for one vehicle.  Returns the degradation (SOH loss).
-template <typename IdxT>
-__device__ __noinline__ double sei_eval(const StepParams& p, size_t i, const double* __restrict__ hcol, int len,
-                                        RfStack<IdxT> st) {
+// RainflowSeiDegradation.calculate_degradation for one vehicle, given pass 1's result.  Returns the SOH loss.
+__device__ __forceinline__ double sei_finish(const StepParams& p, size_t i, const double* __restrict__ x, int xstride,
+                                             int len, const RfOut r, const uint32_t* __restrict__ recs) {
     const double alpha_sei = 5.75E-2, beta_sei = 121, k_sigma = 1.04, sigma_ref = 0.5, k_temp = 6.93E-2,
-                 temp_ref = 25, k_dt = 4.14E-10;
+                 temp_ref = 25, k_dt = 4.14E-10, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
     const int rf_len = p.rf_len[i];
-    SeiAcc acc;
-    acc.m = 0; acc.a = rf_len - 1; acc.mean_sum = 0; acc.fsum = 0; acc.max_dod = 0; acc.have_pending = false;
-    acc.pend_eff = acc.pend_mean = acc.pend_range = 0;
-    acc.s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
-    // With a carried-over rainflow_length the slice is usually empty: count first, evaluate stress only if needed.
-    acc.stress = (rf_len <= 1);
-    rainflow_stream<IdxT>(hcol, p.N, len, st, acc);
-    if (!acc.stress && acc.m > rf_len) {
-        acc.m = 0; acc.mean_sum = 0; acc.fsum = 0; acc.max_dod = 0; acc.have_pending = false; acc.stress = true;
-        rainflow_stream<IdxT>(hcol, p.N, len, st, acc);
-    }
-    const int m = acc.m;
+    const int m = r.m;
     p.n_cycles[i] = m;
     double deg = 0;
     if (m > rf_len) {                                                                  // :143
+        const double s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
+        double fsum = 0, max_dod = 0;
+        for (int j = rf_len - 1; j < m - 1; j++) {                                     // iloc[rf_len-1 : len-1], :146
+            const uint32_t rec = recs[j * kPostThreads];
+            const double xa = x[(size_t)(rec & 0x7fffu) * xstride], xb = x[(size_t)((rec >> 15) & 0x7fffu) * xstride];
+            const double range = fabs(xa - xb), mean = 0.5 * (xa + xb);
+            double eff = range * ((rec >> 30) ? 1.0 : 0.5);                            // :170
+            eff = eff < 0 ? 0 : (eff > 1 ? 1 : eff);
+            const double s_dod = 1.0 / (kd1 * pow(eff, kd2) + kd3);                    // :68  (dod == 0 -> inf -> 0)
+            const double s_soc = exp(k_sigma * (mean - sigma_ref));                    // :70
+            fsum += s_dod * s_soc * s_temp;                                            // :77-79, np.sum :174
+            if (range > max_dod) max_dod = range;
+        }
         const double battery_age = (double)(len - 1) * p.dt * 3600;                    // :138  max(End) == len-1
-        const double mean_soc_cal = acc.mean_sum / (double)m;                          // :140
-        if (acc.max_dod > 5) atomicOr(p.err_flags, 4u);                                // :164-167
-        const double fd_cal = (k_dt * battery_age) * exp(k_sigma * (mean_soc_cal - sigma_ref)) * acc.s_temp;  // :81-83
-        const double fd_cyc = p.fd_cyc[i] + acc.fsum;                                  // :174
+        const double mean_soc_cal = r.mean_sum / (double)m;                            // :140
+        if (max_dod > 5) atomicOr(p.err_flags, 4u);                                    // :164-167
+        const double fd_cal = (k_dt * battery_age) * exp(k_sigma * (mean_soc_cal - sigma_ref)) * s_temp;  // :81-83
+        const double fd_cyc = p.fd_cyc[i] + fsum;                                      // :174
         p.fd_cyc[i] = fd_cyc;
         const double fd = fd_cyc + fd_cal;
         const double l_old = p.life[i];
@@ -370,9 +399,9 @@ __device__ __noinline__ double sei_eval(const StepParams& p, size_t i, const dou
 }
 
 // EmpiricalDegradation.calculate_degradation for one vehicle (empirical_degradation.py:60-94).
-__device__ __forceinline__ double empirical_eval(const StepParams& p, const double* __restrict__ hcol, int len) {
-    const double old_soc = hcol[(size_t)(len - 2) * p.N];
-    const double new_soc = hcol[(size_t)(len - 1) * p.N];
+__device__ __forceinline__ double empirical_eval(double dt, double evse, int N, const double* __restrict__ hcol, int len) {
+    const double old_soc = hcol[(size_t)(len - 2) * N];
+    const double new_soc = hcol[(size_t)(len - 1) * N];
     const double avg_soc = (old_soc + new_soc) / 2;
     const double cs[3] = {0, 40, 90};
     const double ca[3] = {0.0065, 0.0293, 0.065};
@@ -383,34 +412,61 @@ __device__ __forceinline__ double empirical_eval(const StepParams& p, const doub
         const double d = fabs(cs[k] - avg_soc);
         if (d < bd) { bd = d; best = k; }
     }
-    const double cal = ca[best] * p.dt / 8760;
+    const double cal = ca[best] * dt / 8760;
     const double dod = fabs(new_soc - old_soc);
-    const double cyc = (p.evse <= 22.0) ? dod * 0.000125 / 2 : dod * 0.000167 / 2;
+    const double cyc = (evse <= 22.0) ? dod * 0.000125 / 2 : dod * 0.000167 / 2;
     return cal + cyc;
 }
 
-// ------------------------------------------------------------------------------------------------ step kernel
-// Shared-memory layout (dynamic): EnvS envs[B] | double contrib[kNQ][slots] | double sums[kNSum][B] | index stack
-__host__ __device__ inline size_t smem_envs_bytes(int B) { return ((size_t)B * sizeof(EnvS) + 15) & ~(size_t)15; }
+// --------------------------------------------------------------------------------------- TMA bulk store helpers
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    // make the generic-proxy shared-memory writes visible to the async proxy, then one bulk copy (UBLKCP)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
 
-template <bool kNorm, bool kAux, typename IdxT>
-__global__ void __launch_bounds__(kThreads) fleet_step_kernel(const StepParams p) {
+// ------------------------------------------------------------------------------------------------ step kernel
+// Work-list entry pushed by the step kernel for envs that need the post kernel (daily degradation and/or reset).
+constexpr int WL_TRIGGER = 1, WL_RESET = 2;
+
+// Shared-memory layout (dynamic): EnvS envs[B] | double contrib[kNQ][slots] | double sums[kNQ][B] |
+//                                 float obs_tile[B][D] (16-byte aligned)
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t smem_envs_bytes(int B) { return align16((size_t)B * sizeof(EnvS)); }
+__host__ __device__ inline size_t smem_obs_offset(int B, int N) {
+    return align16(smem_envs_bytes(B) + (size_t)kNQ * B * N * 8 + (size_t)kNQ * B * 8);
+}
+__host__ __device__ inline size_t smem_step_bytes(int B, int N, int D) {
+    return align16(smem_obs_offset(B, N) + (size_t)B * D * 4);
+}
+
+template <bool kNorm, bool kAux>
+__global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = p.N, B = p.B;
+    const int N = p.N, B = p.B, D = p.D;
     EnvS* envs = reinterpret_cast<EnvS*>(smem_raw);
-    double* contrib = reinterpret_cast<double*>(smem_raw + smem_envs_bytes(B));
+    double* contrib = reinterpret_cast<double*>(smem_raw + p.off_contrib);
     const int cstride = B * N;  // contrib[q][slot]
-    double* sums = contrib + (size_t)kNQ * cstride;
-    IdxT* stack_base = reinterpret_cast<IdxT*>(sums + (size_t)kNSum * B);
-    __shared__ int s_any;  // bit0: some env triggered degradation, bit1: some env auto-resets
+    double* sums = contrib + kNQ * cstride;
+    float* obs_tile = reinterpret_cast<float*>(smem_raw + p.off_obs);
+    __shared__ int s_any;       // bit1: some env of the tile finished and auto-resets (its row goes to terminal_obs)
 
     const int tid = threadIdx.x;
     const int e0 = blockIdx.x * B;
     const int nb = min(B, p.E - e0);
     const int nslots = nb * N;
+    const int npass = (nslots + kThreads - 1) / kThreads;   // 1 unless N > kThreads
+    const int H = p.Ha + p.Hb;
 
-    // ---- P0: one thread per env: time index, per-time factors, destination of the observation row
     if (tid == 0) s_any = 0;
+    __syncthreads();
+
+    // ---- P0: one thread per env: time index, per-time factors, flags
     if (tid < nb) {
         const int e = e0 + tid;
         const int4 ev = p.env4[e];
@@ -434,181 +490,225 @@ __global__ void __launch_bounds__(kThreads) fleet_step_kernel(const StepParams p
             if ((fl & EF_DONE) && p.auto_reset) fl |= EF_RESET;
         }
         es.flags = fl;
-        // SB3 semantics: a finished env returns the first observation of its next episode in obs and the last
-        // observation of the finished one in infos["terminal_observation"].
-        if (fl & EF_RESET) es.obs_dst = p.terminal_obs ? p.terminal_obs + (size_t)e * p.D : nullptr;
-        else es.obs_dst = p.obs ? p.obs + (size_t)e * p.D : nullptr;
-        es.deg_sum = 0;
-        es.t0_new = 0;
-        int any = 0;
-        if (fl & EF_TRIGGER) any |= 1;
-        if (fl & EF_RESET) any |= 2;
-        if (any) atomicOr(&s_any, any);
+        // SB3 semantics: a finished env returns the first observation of its next episode in obs (written by the
+        // post kernel) and the last observation of the finished one in infos["terminal_observation"].
+        if (fl & EF_RESET) es.obs_dst = p.terminal_obs ? p.terminal_obs + (size_t)e * D : nullptr;
+        else es.obs_dst = p.obs ? p.obs + (size_t)e * D : nullptr;
+        if (fl & EF_RESET) atomicOr(&s_any, 2);
     }
-    __syncthreads();
 
     const bool have_flips = (*p.n_flips != 0);
-
-    // ---- P1: one thread per (env, EV): charge / discharge, transition, per-EV observation parts
-    for (int j = tid; j < nslots; j += kThreads) {
-        const int b = j / N, n = j - b * N;
-        const EnvS& es = envs[b];
-        const int e = e0 + b;
-        const size_t i = (size_t)e * N + n;
-        double c_cost = 0, c_rev = 0, c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_ath = 0, c_miss = 0, c_dep = 0;
-        if (es.flags & EF_FROZEN) {
-            if (es.obs_dst) {
-                const EvRec rec = load_rec(&p.ev_rec[(size_t)min(es.t, p.T - 1) * N + n]);
-                const bool flip = have_flips && p.tflip[i] != 0;
-                write_ev_obs<kNorm, kAux>(p, es.obs_dst, n, p.soc[i], p.hl[i], rec, flip ? 0.9 : p.target);
-                copy_hdr<kAux>(p, es.obs_dst, n, min(es.t, p.T - 1));
-            }
-        } else {
-            const int t = es.t;
-            const int k = t - es.t_start;
-            const float a32 = p.actions[i];
-            double soc = p.soc[i];
-            float hl = p.hl[i];
-            const double soh = p.soh[i];
-            double sdeg = p.hist[((size_t)e * p.R + (k % p.R)) * N + n];
-            const EvRec rec = load_rec(&p.ev_rec[(size_t)min(t + 1, p.T - 1) * N + n]);
-            const bool flip = have_flips && p.tflip[i] != 0;
-            const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
-            const double cap = soh * p.cap0;                                // episode.battery_cap[car]
-            const int there = rec.there_prev;                               // db.There at t
-            const double a = (double)a32;
-            double nsoc = soc;
-            if (a >= 0) {                                                   // ev_charger.py:98-156
-                const double dem = (tgt - soc) * cap;
-                const double req = p.P * a * p.dt;
-                if (req * p.eta_c > dem) {
-                    const double d = req - dem;
-                    const double pen = p.pen_oc * (d * d);
-                    c_oc = pen > p.clip_oc ? pen : p.clip_oc;
-                }
-                double en;
-                if (there == 1) en = fmin(dem / p.eta_c, req);
-                else {
-                    en = 0;
-                    if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
-                }
-                nsoc = soc + en * p.eta_c / cap;
-                double ge = en - es.pv_share;
-                ge = ge > 0 ? ge : 0;
-                c_cost = ge * es.S * p.mult;
-                c_cr = es.F_cr * ge;
-            } else if (a < 0) {                                             // ev_charger.py:159-206
-                const double left = -1 * soc * cap;
-                const double req = p.P * a * p.dt;
-                if (req * p.eta_d < left && there != 0) {
-                    const double d = left - req;
-                    c_oc = p.pen_oc * (d * d);
-                }
-                double en;
-                if (there == 1) en = fmax(left, req);
-                else {
-                    en = 0.0;
-                    if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
-                }
-                nsoc = soc + en / cap;
-                c_rev = -1 * en * es.Rfac;
-                c_dr = es.F_dr * en;
-            } else {
-                atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
-            }
-            c_ath = a * (double)there;                                      // fleet_environment.py:491
-            soc = nsoc;                                                     // :470
-
-            // time has advanced to t+1: departure / still there / gone / arrival   :528-618
-            const float ntl = rec.tl;
-            if (hl != 0.f && ntl == 0.f) {
-                const double tg = (p.is_ct && (es.flags & EF_LUNCH)) ? p.target_lunch : tgt;
-                const double diff = tg - soc;
-                if (diff > p.eps) {
-                    c_miss = diff;
-                    c_dep = -500 / (1 + exp(-16.48461585 * (diff - 0.29229767))) + 1;   // score_config.py:26-30
-                } else {
-                    c_dep = p.full_reward;
-                }
-            }
-            if (ntl != 0.f && hl != 0.f) hl -= p.dt_f;
-            else { hl = ntl; soc = rec.sr; }
-            if (soh <= 0.9 && !flip) {                                      // :613-614 (visible from the next step on)
-                p.tflip[i] = 1;
-                atomicAdd(p.n_flips, 1);
-            }
-            if (hl != 0.f) sdeg = soc;                                      // :621-623
-
-            p.soc[i] = soc;
-            p.hl[i] = hl;
-            p.hist[((size_t)e * p.R + ((k + 1) % p.R)) * N + n] = sdeg;     // log_soc, :655-656
-            if (es.obs_dst) {
-                write_ev_obs<kNorm, kAux>(p, es.obs_dst, n, soc, hl, rec, tgt);
-                copy_hdr<kAux>(p, es.obs_dst, n, min(t + 1, p.T - 1));
-            }
+    int any = 0;
+    for (int pass = 0; pass < npass; pass++) {
+        // ---- P1a: one thread per (env, EV): issue every load before the barrier.  The slot reads its env's
+        // time index itself (one broadcast 128-bit load) so that the schedule record and the history row do not
+        // wait for P0.
+        const int j = pass * kThreads + tid;
+        const bool active = j < nslots;
+        int b = 0, n = 0, t = 0, k = 0;
+        size_t i = 0, hrow = 0;
+        float a32 = 0.f, hl = 0.f;
+        double soc = 0, soh = 1, sdeg = 0;
+        EvRec rec;
+        rec.sr = 0; rec.tl = 0; rec.there = rec.there_prev = 0; rec.pad = 0; rec.tt = rec.cl = rec.hn = rec.lax = 0;
+        if (active) {
+            b = (N == 1) ? j : (int)__umulhi((unsigned)j, p.n_magic);
+            n = j - b * N;
+            const int e = e0 + b;
+            i = (size_t)e0 * N + j;
+            const int4 ev = p.env4[e];
+            t = ev.x; k = ev.x - ev.y;
+            a32 = __ldcs(p.actions + i);
+            soc = __ldcs(p.soc + i);
+            hl = __ldcs(p.hl + i);
+            soh = __ldcs(p.soh + i);
+            hrow = (size_t)e * p.RN + (unsigned)((p.calc_deg ? k : (k & 1)) * N + n);
+            sdeg = __ldcs(p.hist + hrow);
+            const int tr = (!p.auto_reset && k >= p.L) ? min(t, p.T - 1) : min(t + 1, p.T - 1);   // frozen: row t
+            rec = load_rec(&p.ev_rec[(size_t)tr * N + n]);
         }
-        contrib[Q_COST * cstride + j] = c_cost; contrib[Q_REV * cstride + j] = c_rev;
-        contrib[Q_CR * cstride + j] = c_cr;     contrib[Q_DR * cstride + j] = c_dr;
-        contrib[Q_INV * cstride + j] = c_inv;   contrib[Q_OC * cstride + j] = c_oc;
-        contrib[Q_ATH * cstride + j] = c_ath;   contrib[Q_MISS * cstride + j] = c_miss;
-        contrib[Q_DEP * cstride + j] = c_dep;
+        if (pass == 0) {
+            __syncthreads();
+            any = s_any;
+        }
+        // time-only part of the observation: host-precomputed float32 row per time index, one element per thread
+        float hv = 0.f; int hdst = -1;
+        if (pass == 0 && tid < nb * H) {
+            const int bb = (H == 1) ? tid : (int)__umulhi((unsigned)tid, p.h_magic), q = tid - bb * H;
+            const EnvS& eh = envs[bb];
+            const int th = (eh.flags & EF_FROZEN) ? min(eh.t, p.T - 1) : min(eh.t + 1, p.T - 1);
+            hv = __ldg(p.hdr + (size_t)th * p.hdr_stride + q);
+            hdst = bb * D + (q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha));
+        }
+
+        // ---- P1b: charge / discharge, transition, per-EV observation parts (into the shared obs tile)
+        if (active) {
+            const EnvS& es = envs[b];
+            float* orow = obs_tile + b * D;
+            double c_rew = 0, c_cash = 0, c_ath = 0, c_miss = 0, c_nviol = 0;
+            const bool flip = have_flips && p.tflip[i] != 0;
+            if (!(es.flags & EF_FROZEN)) {
+                const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
+                const double cap = soh * p.cap0;                                // episode.battery_cap[car]
+                const int there = rec.there_prev;                               // db.There at t
+                const double a = (double)a32;
+                double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0;
+                double num = 0;                                                 // next_soc = soc + num / cap
+                if (a >= 0) {                                                   // ev_charger.py:98-156
+                    const double dem = (tgt - soc) * cap;
+                    const double req = p.P * a * p.dt;
+                    if (req * p.eta_c > dem) {
+                        const double d = req - dem;
+                        const double pen = p.pen_oc * (d * d);
+                        c_oc = pen > p.clip_oc ? pen : p.clip_oc;
+                    }
+                    double en = 0;
+                    if (there == 1) {
+                        double q;                                               // dem / eta_c, correctly rounded
+                        if (p.eta_c_rcp_ok) {
+                            const double q0 = dem * p.eta_c_rcp;                // Markstein: r = RN(1/b); q0 = RN(a r);
+                            const double rem = fma(-q0, p.eta_c, dem);          // rem = a - q0 b (exact);
+                            q = fma(rem, p.eta_c_rcp, q0);                      // q = RN(q0 + rem r)
+                        } else {
+                            q = dem / p.eta_c;
+                        }
+                        en = fmin(q, req);
+                    } else if (fabs(a) > 0.05) {
+                        c_inv = p.pen_inv * (a * a);
+                    }
+                    num = en * p.eta_c;
+                    double ge = en - es.pv_share;
+                    ge = ge > 0 ? ge : 0;
+                    c_cost = ge * es.S * p.mult;
+                    c_cr = es.F_cr * ge;
+                } else if (a < 0) {                                             // ev_charger.py:159-206
+                    const double left = -1 * soc * cap;
+                    const double req = p.P * a * p.dt;
+                    if (req * p.eta_d < left && there != 0) {
+                        const double d = left - req;
+                        c_oc = p.pen_oc * (d * d);
+                    }
+                    double en = 0.0;
+                    if (there == 1) en = fmax(left, req);
+                    else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
+                    num = en;
+                    c_rev = -1 * en * es.Rfac;
+                    c_dr = es.F_dr * en;
+                } else {
+                    atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
+                }
+                c_ath = a * (double)there;                                      // fleet_environment.py:491
+                // ev_charger.py:128,189 ; :470.  num == 0 (absent vehicle, zero action) adds exactly 0: skipping the
+                // division there is bit-identical and keeps the warp out of the slow path of the f64 divide.
+                if (num != 0) soc = soc + num / cap;
+
+                // time has advanced to t+1: departure / still there / gone / arrival   :528-618
+                const float ntl = rec.tl;
+                if (hl != 0.f && ntl == 0.f) {
+                    const double tg = (p.is_ct && (es.flags & EF_LUNCH)) ? p.target_lunch : tgt;
+                    const double diff = tg - soc;
+                    if (diff > p.eps) {
+                        c_miss = diff; c_nviol = 1;
+                        c_dep = -500 / (1 + exp(-16.48461585 * (diff - 0.29229767))) + 1;   // score_config.py:26-30
+                    } else {
+                        c_dep = p.full_reward;
+                    }
+                }
+                if (ntl != 0.f && hl != 0.f) hl -= p.dt_f;
+                else { hl = ntl; soc = rec.sr; }
+                if (soh <= 0.9 && !flip) {                                      // :613-614 (visible from the next step on)
+                    p.tflip[i] = 1;
+                    atomicAdd(p.n_flips, 1);
+                }
+                if (hl != 0.f) sdeg = soc;                                      // :621-623
+
+                __stcs(p.soc + i, soc);
+                __stcs(p.hl + i, hl);
+                const size_t hnext = p.calc_deg ? hrow + N : (hrow - (size_t)(k & 1) * N + (size_t)((k + 1) & 1) * N);
+                __stcs(p.hist + hnext, sdeg);                                   // log_soc, :655-656
+                c_rew = c_cr + c_dr + c_inv + c_oc + c_dep;                     // per-vehicle reward terms (:228,548-590)
+                c_cash = -1 * c_cost + c_rev;                                   // ev_charger.py:225
+            }
+            write_ev_obs<kNorm, kAux>(p, orow, n, soc, hl, rec, flip);
+            contrib[Q_REWARD * cstride + j] = c_rew;  contrib[Q_CASH * cstride + j] = c_cash;
+            contrib[Q_ATH * cstride + j] = c_ath;     contrib[Q_MISS * cstride + j] = c_miss;
+            contrib[Q_NVIOL * cstride + j] = c_nviol;
+        }
+        if (hdst >= 0) obs_tile[hdst] = hv;
+    }
+    // remaining header elements when the tile holds more than kThreads of them (small N)
+    for (int w = kThreads + tid; w < nb * H; w += kThreads) {
+        const int bb = w / H, q = w - bb * H;
+        const EnvS& eh = envs[bb];
+        const int th = (eh.flags & EF_FROZEN) ? min(eh.t, p.T - 1) : min(eh.t + 1, p.T - 1);
+        obs_tile[bb * D + (q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha))] =
+            __ldg(p.hdr + (size_t)th * p.hdr_stride + q);
     }
     __syncthreads();
 
-    // ---- P2: one thread per (quantity, env): sequential sum over the env's EVs in car order
-    for (int w = tid; w < kNSum * nb; w += kThreads) {
-        const int q = w / nb, b = w - q * nb;
-        const double* c = contrib + (size_t)q * cstride + (size_t)b * N;
+    // ---- observation tile -> HBM: one TMA bulk store per CTA when every row goes to obs[e0 .. e0+nb)
+    const bool use_bulk = p.bulk_ok && nb == B && !(any & 2) && p.obs != nullptr;
+    if (use_bulk) {
+        if (tid == 0) bulk_store_s2g(p.obs + (size_t)e0 * D, obs_tile, (uint32_t)(B * D * 4));
+    } else {
+        for (int w = tid; w < nb * D; w += kThreads) {
+            const int bb = w / D;
+            float* dst = envs[bb].obs_dst;
+            if (dst) dst[w - bb * D] = obs_tile[w];
+        }
+    }
+
+    // ---- P2: one thread per (quantity, env): sequential sum over the env's EVs in car order (deterministic)
+    for (int w = tid; w < kNQ * nb; w += kThreads) {
+        const int q = w / nb, bb = w - q * nb;
+        const double* c = contrib + q * cstride + bb * N;
         double s = 0;
-        for (int n = 0; n < N; n++) s += c[n];
-        sums[q * B + b] = s;
+#pragma unroll 10
+        for (int nn = 0; nn < N; nn++) s += c[nn];
+        sums[q * B + bb] = s;
     }
     __syncthreads();
 
-    // ---- P3: one thread per env: cashflow, reward, overload penalty, departure terms, done, statistics
-    double st_loc[FLEET_S__COUNT];
-#pragma unroll
-    for (int q = 0; q < FLEET_S__COUNT; q++) st_loc[q] = 0;
+    // ---- P3: one thread per env: cashflow, reward, overload penalty, done, statistics, work list
     if (tid < nb) {
-        const int b = tid, e = e0 + b;
-        EnvS& es = envs[b];
+        const int bb = tid, e = e0 + bb;
+        const EnvS& es = envs[bb];
         double reward = 0, cashflow = 0, overload = 0, soc_viol = 0;
         int done = 0;
+        double* st = p.stats + (size_t)(blockIdx.x % kStatStripes) * FLEET_S__COUNT;
         if (es.flags & EF_FROZEN) {
             done = 1;
         } else {
-            cashflow = -1 * sums[Q_COST * B + b] + sums[Q_REV * B + b];                        // ev_charger.py:225
-            reward = sums[Q_CR * B + b] + sums[Q_DR * B + b] + sums[Q_INV * B + b] + sums[Q_OC * B + b];  // :228
-            const double margin = es.gml - sums[Q_ATH * B + b] * p.evse + es.pvv;              // load_calculation.py:93
+            cashflow = sums[Q_CASH * B + bb];
+            reward = sums[Q_REWARD * B + bb];
+            const double margin = es.gml - sums[Q_ATH * B + bb] * p.evse + es.pvv;             // load_calculation.py:93
             overload = fabs(margin < 0.0 ? margin : 0.0);
             if (overload > 0) {
                 const double rel = overload / p.grid + 1;                                      // fleet_environment.py:496
                 const double pen = (rel < 1.1) ? 0.0 : -700 / (1 + exp(-15.77350877 * (rel - 1.33298382)));
                 reward += pen * p.pen_ovl;                                                     // score_config.py:33-41
+                atomicAdd(st + FLEET_S_OVERLOAD_KW, overload);
             }
-            const double* cd = contrib + (size_t)Q_DEP * cstride + (size_t)b * N;
-            const double* cm = contrib + (size_t)Q_MISS * cstride + (size_t)b * N;
-            int n_viol = 0;
-            for (int n = 0; n < N; n++) { reward += cd[n]; n_viol += (cm[n] > 0) ? 1 : 0; }  // :548,554,583,590
-            soc_viol = fabs(sums[Q_MISS * B + b]);                                             // :661
+            soc_viol = fabs(sums[Q_MISS * B + bb]);                                            // :661
+            const double n_viol = sums[Q_NVIOL * B + bb];
             done = (es.flags & EF_DONE) ? 1 : 0;                                               // :627-628
-            double ep_ret = p.env_f64[(size_t)EF_EP_RETURN * p.E + e] + reward;                // :637
-            st_loc[FLEET_S_STEPS] = 1; st_loc[FLEET_S_REWARD] = reward; st_loc[FLEET_S_CASHFLOW] = cashflow;
-            st_loc[FLEET_S_PENALTY] = reward - (cashflow * p.price_mult);                      // :659
-            st_loc[FLEET_S_OVERLOAD_KW] = overload; st_loc[FLEET_S_SOC_VIOL] = soc_viol;
-            st_loc[FLEET_S_N_VIOL] = n_viol;
-            int t_new = es.t + 1, t_start = es.t_start, ep_count = es.ep_count;
+            const double ep_ret = p.env_f64[(size_t)EF_EP_RETURN * p.E + e] + reward;          // :637
+            atomicAdd(st + FLEET_S_STEPS, 1.0);
+            atomicAdd(st + FLEET_S_REWARD, reward);
+            atomicAdd(st + FLEET_S_CASHFLOW, cashflow);
+            if (n_viol > 0) { atomicAdd(st + FLEET_S_SOC_VIOL, soc_viol); atomicAdd(st + FLEET_S_N_VIOL, n_viol); }
             if (done) {
-                st_loc[FLEET_S_EPISODES] = 1; st_loc[FLEET_S_EP_RETURN] = ep_ret;
+                atomicAdd(st + FLEET_S_EPISODES, 1.0);
+                atomicAdd(st + FLEET_S_EP_RETURN, ep_ret);
                 p.env_f64[(size_t)EF_LAST_EP_RETURN * p.E + e] = ep_ret;
-                if (es.flags & EF_RESET) {
-                    const int t0 = p.next_start ? p.next_start[e] : draw_start(p, p.env_id_offset + e, ep_count);
-                    es.t0_new = t0;
-                    t_new = t0; t_start = t0; ep_count += 1; ep_ret = 0;
-                }
             }
             p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
-            p.env4[e] = make_int4(t_new, t_start, ep_count, 0);
+            p.env4[e] = make_int4(es.t + 1, es.t_start, es.ep_count, 0);
+            const int wf = ((es.flags & EF_TRIGGER) ? WL_TRIGGER : 0) | ((es.flags & EF_RESET) ? WL_RESET : 0);
+            if (wf) {   // the post kernel evaluates the degradation first and resets afterwards, like the reference
+                const int slot = atomicAdd(p.wl_count, 1);
+                p.wl[slot] = make_int2(e, wf);
+            }
         }
         p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
         p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
@@ -617,61 +717,88 @@ __global__ void __launch_bounds__(kThreads) fleet_step_kernel(const StepParams p
         if (p.reward) p.reward[e] = (float)reward;
         if (p.done) p.done[e] = (uint8_t)done;
     }
+    if (use_bulk && tid == 0) bulk_store_wait_read();   // the tile must stay valid until the bulk copy has read it
+}
 
-    // ---- P4: daily degradation for the envs of the tile whose new time is 14:45   fleet_environment.py:665-673
-    const int any = s_any;  // written before the first barrier, stable since
-    if (any & 1) {
-        for (int j = tid; j < nslots; j += kThreads) {
-            const int b = j / N, n = j - b * N;
-            EnvS& es = envs[b];
-            if (!(es.flags & EF_TRIGGER)) continue;
-            const int e = e0 + b;
-            const size_t i = (size_t)e * N + n;
-            const int len = es.t - es.t_start + 2;  // history rows 0..k+1
-            const double* hcol = p.hist + (size_t)e * p.R * N + n;
-            double deg;
-            if (p.deg_mode == FLEET_DEG_EMPIRICAL) {
-                deg = empirical_eval(p, hcol, len);
-                p.n_cycles[i] = 0;
-            } else {
-                RfStack<IdxT> st;
-                st.s = stack_base + (j % kThreads);
-                st.stride = kThreads;
-                deg = sei_eval<IdxT>(p, i, hcol, len, st);
+// ------------------------------------------------------------------------------------------------ post kernel
+// One CTA of kPostThreads threads per work-list env (persistent loop over the list): first the daily degradation
+// (fleet_environment.py:665-673), then — if the episode finished and auto-reset is on — FleetEnv.reset
+// (:330-434), i.e. the order in which a SubprocVecEnv worker runs them.  The env's SOC history (<= L+1 rows of N
+// doubles) is first staged into shared memory with coalesced, deeply unrolled loads; each thread then streams its
+// vehicle's column through the three-point rainflow with an index stack in shared memory.
+__host__ __device__ inline size_t post_smem_bytes(int cap) {
+    // value ring [kStackS][64] f64 | batch staging [kRfBatch][64] f64 | index ring [kStackS][64] u16 | records [cap][64] u32
+    return align16((size_t)kStackS * kPostThreads * 8 + (size_t)kRfBatch * kPostThreads * 8 + (size_t)kStackS * kPostThreads * 2 +
+                   (size_t)cap * kPostThreads * 4);
+}
+
+template <bool kNorm, bool kAux>
+__global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.N, D = p.D;
+    double* vring = reinterpret_cast<double*>(smem_raw);
+    double* xstage = vring + kStackS * kPostThreads;
+    uint16_t* iring = reinterpret_cast<uint16_t*>(xstage + kRfBatch * kPostThreads);
+    uint32_t* recs = reinterpret_cast<uint32_t*>(iring + kStackS * kPostThreads);
+    __shared__ double s_deg;
+    const int tid = threadIdx.x;
+    const int count = *p.wl_count;
+
+    for (int w = blockIdx.x; w < count; w += gridDim.x) {
+        const int2 ent = p.wl[w];
+        const int e = ent.x, wf = ent.y;
+        const int4 ev = p.env4[e];                      // {t (already advanced), t_start, ep_count}
+        const int len = ev.x - ev.y + 1;                // history rows 0..k+1 where k+1 = t - t_start
+        if (wf & WL_TRIGGER) {
+            if (tid == 0) s_deg = 0;
+            __syncthreads();
+            for (int n0 = 0; n0 < N; n0 += kPostThreads) {
+                const int n = n0 + tid;
+                if (n < N) {
+                    const size_t ii = (size_t)e * N + n;
+                    const double* hcol = p.hist + (size_t)e * p.R * N + n;
+                    double deg;
+                    if (p.deg_mode == FLEET_DEG_EMPIRICAL) {
+                        deg = empirical_eval(p.dt, p.evse, N, hcol, len);
+                        p.n_cycles[ii] = 0;
+                    } else {
+                        RfRing rg; rg.v = vring + tid; rg.i = iring + tid; rg.mask = kStackS - 1; rg.stride = kPostThreads;
+                        RfOut r = rainflow_pass1<true>(hcol, N, len, rg, recs + tid, xstage + tid);
+                        if (r.overflow) {   // stack deeper than the shared ring: redo with the global scratch ring
+                            RfRing gg;
+                            gg.v = p.post_scratch_v + ((size_t)blockIdx.x * p.scratch_cap) * kPostThreads + tid;
+                            gg.i = p.post_scratch_i + ((size_t)blockIdx.x * p.scratch_cap) * kPostThreads + tid;
+                            gg.mask = p.scratch_cap - 1; gg.stride = kPostThreads;
+                            r = rainflow_pass1<false>(hcol, N, len, gg, recs + tid, xstage + tid);
+                        }
+                        deg = sei_finish(p, ii, hcol, N, len, r, recs + tid);
+                    }
+                    p.last_deg[ii] = deg;
+                    p.soh[ii] = p.soh[ii] - deg;                                // :671 (battery_cap is derived, :673)
+                    if (deg != 0) atomicAdd(&s_deg, deg);
+                }
             }
-            p.last_deg[i] = deg;
-            p.soh[i] = p.soh[i] - deg;                                      // :671 (battery_cap is derived, :673)
-            atomicAdd(&es.deg_sum, deg);
+            __syncthreads();
+            if (tid == 0 && s_deg != 0)
+                atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
+        }
+        if (wf & WL_RESET) {
+            const int t0 = p.next_start ? p.next_start[e]
+                                        : draw_start(p.seed, p.start_lo, p.start_hi, p.env_id_offset + e, ev.z);
+            for (int n = tid; n < N; n += kPostThreads)
+                reset_slot<kNorm, kAux>(p, e, n, t0, p.obs ? p.obs + (size_t)e * D : nullptr, !p.carry);
+            if (tid == 0) {
+                p.env4[e] = make_int4(t0, t0, ev.z + 1, 0);
+                p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = 0;
+            }
         }
         __syncthreads();
-        if (tid < nb) st_loc[FLEET_S_DEGRADATION] = envs[tid].deg_sum;
     }
-
-    // statistics: warp reduce over the env threads, one striped atomic per warp and quantity
-    if (tid < ((nb + 31) & ~31)) {
-#pragma unroll
-        for (int q = 0; q < FLEET_S__COUNT; q++) {
-            double v = st_loc[q];
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((tid & 31) == 0 && v != 0)
-                atomicAdd(p.stats + (size_t)((blockIdx.x + (tid >> 5)) % kStatStripes) * FLEET_S__COUNT + q, v);
-        }
-    }
-
-    // ---- P5: auto-reset of finished envs (SubprocVecEnv worker: reset right after a done step)
-    if (any & 2) {
-        __syncthreads();
-        for (int j = tid; j < nslots; j += kThreads) {
-            const int b = j / N, n = j - b * N;
-            const EnvS& es = envs[b];
-            if (!(es.flags & EF_RESET)) continue;
-            const int e = e0 + b;
-            reset_slot<kNorm, kAux>(p, e, n, es.t0_new, p.obs ? p.obs + (size_t)e * p.D : nullptr, !p.carry);
-        }
+    // the last CTA to finish clears the work list for the next step
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int d = atomicAdd(p.wl_done, 1u);
+        if (d == gridDim.x - 1) { *p.wl_count = 0; *p.wl_done = 0; }
     }
 }
 
@@ -686,7 +813,7 @@ __global__ void __launch_bounds__(kThreads) fleet_reset_kernel(const StepParams 
         const int e = e0 + b;
         if (p.mask && !p.mask[e]) continue;
         const int4 ev = p.env4[e];
-        const int t0 = p.start_idx ? p.start_idx[e] : draw_start(p, p.env_id_offset + e, ev.z);
+        const int t0 = p.start_idx ? p.start_idx[e] : draw_start(p.seed, p.start_lo, p.start_hi, p.env_id_offset + e, ev.z);
         reset_slot<kNorm, kAux>(p, e, n, t0, p.obs ? p.obs + (size_t)e * p.D : nullptr, !p.carry);
     }
     __syncthreads();  // all slots have read env4 before it is rewritten
@@ -694,7 +821,7 @@ __global__ void __launch_bounds__(kThreads) fleet_reset_kernel(const StepParams 
         const int e = e0 + threadIdx.x;
         if (!(p.mask && !p.mask[e])) {
             const int4 ev = p.env4[e];
-            const int t0 = p.start_idx ? p.start_idx[e] : draw_start(p, p.env_id_offset + e, ev.z);
+            const int t0 = p.start_idx ? p.start_idx[e] : draw_start(p.seed, p.start_lo, p.start_hi, p.env_id_offset + e, ev.z);
             p.env4[e] = make_int4(t0, t0, ev.z + 1, 0);
             p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = 0;
         }
@@ -745,13 +872,17 @@ __global__ void scatter_target_kernel(StepParams p, const double* src) {
     }
 }
 
-__global__ void reduce_stats_kernel(const double* stats, double* dst) {
+__global__ void reduce_stats_kernel(const double* stats, double* dst, double price_mult) {
+    __shared__ double tot[FLEET_S__COUNT];
     const int q = threadIdx.x;
     if (q < FLEET_S__COUNT) {
         double s = 0;
         for (int k = 0; k < kStatStripes; k++) s += stats[(size_t)k * FLEET_S__COUNT + q];
-        dst[q] = s;
+        tot[q] = s;
     }
+    __syncthreads();
+    if (q < FLEET_S__COUNT)   // penalty = reward - cashflow*price_multiplier is linear, so its sum is derived (:659)
+        dst[q] = (q == FLEET_S_PENALTY) ? tot[FLEET_S_REWARD] - tot[FLEET_S_CASHFLOW] * price_mult : tot[q];
 }
 
 }  // namespace
@@ -767,8 +898,8 @@ struct FleetHandle {
     int64_t bytes = 0;
     int64_t launches = 0;
     std::string err;
-    size_t smem_step = 0;
-    int grid = 0;
+    size_t smem_step = 0, smem_post = 0;
+    int grid = 0, grid_post = 0, need_post = 0, num_sms = 0;
     int max_smem_optin = 0;
     // host-call staging (fleet_step_host)
     float* h_actions_dev = nullptr; float* h_obs_dev = nullptr; float* h_reward_dev = nullptr; uint8_t* h_done_dev = nullptr;
@@ -830,13 +961,13 @@ inline int look_idx(const FleetConsts& c, const FleetTables& tb, int t, int k) {
 
 using StepKernel = void (*)(const StepParams);
 
-template <typename IdxT>
-StepKernel pick_step(bool norm, bool aux) {
-    if (norm) return aux ? fleet_step_kernel<true, true, IdxT> : fleet_step_kernel<true, false, IdxT>;
-    return aux ? fleet_step_kernel<false, true, IdxT> : fleet_step_kernel<false, false, IdxT>;
-}
 StepKernel pick_step(const FleetHandle* h) {
-    return h->p.stack_u16 ? pick_step<uint16_t>(h->c.normalize, h->c.aux) : pick_step<uint8_t>(h->c.normalize, h->c.aux);
+    if (h->c.normalize) return h->c.aux ? fleet_step_kernel<true, true> : fleet_step_kernel<true, false>;
+    return h->c.aux ? fleet_step_kernel<false, true> : fleet_step_kernel<false, false>;
+}
+StepKernel pick_post(const FleetHandle* h) {
+    if (h->c.normalize) return h->c.aux ? fleet_post_kernel<true, true> : fleet_post_kernel<true, false>;
+    return h->c.aux ? fleet_post_kernel<false, true> : fleet_post_kernel<false, false>;
 }
 StepKernel pick_reset(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_reset_kernel<true, true> : fleet_reset_kernel<true, false>;
@@ -917,6 +1048,22 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
             r.there = tb->there[(size_t)n * T + t];
             r.there_prev = t > 0 ? tb->there[(size_t)n * T + t - 1] : 0;
             r.pad = 0;
+            // auxiliary observation terms for the configured target SOC (observer_bl_pv.py:85-91), normalised per
+            // oracle_normalization.py:146-150 when requested; float64 in the reference's order, cast once.
+            {
+                const double th = (double)r.there;
+                double tt = (1.0 * c.target_soc) * th;
+                double cl = tt - r.sr;
+                double hn = cl * c.lc_batt_cap / (c.evse_max_power * c.charging_eff);
+                double lax = (tl / (hn + 0.001) - 1) * th;
+                lax = lax < 0 ? 0 : (lax > 5 ? 5 : lax);
+                if (c.normalize) {
+                    const double max_soc = c.target_soc;
+                    const double max_hn = (c.target_soc * c.init_battery_cap) / (c.evse_max_power * c.charging_eff);
+                    tt = tt / max_soc; cl = cl / max_soc; hn = hn / max_hn; lax = lax / 5;
+                }
+                r.tt = (float)tt; r.cl = (float)cl; r.hn = (float)hn; r.lax = (float)lax;
+            }
         }
     }
     std::vector<StepRow> rows((size_t)T);
@@ -1016,9 +1163,13 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     if ((rc = dev_alloc(h, &p.last_deg, EN))) return rc;
     if ((rc = dev_alloc(h, &p.stats, (size_t)kStatStripes * FLEET_S__COUNT))) return rc;
     if ((rc = dev_alloc(h, &p.err_flags, (size_t)4))) return rc;
+    if ((rc = dev_alloc(h, &p.wl, (size_t)E))) return rc;
+    if ((rc = dev_alloc(h, &p.wl_count, (size_t)4))) return rc;
+    if ((rc = dev_alloc(h, &p.wl_done, (size_t)4))) return rc;
 
     p.E = E; p.N = N; p.T = T; p.R = R; p.L = c.episode_steps; p.D = h->D; p.Ha = Ha; p.Hb = Hb; p.hdr_stride = hdr_stride;
     p.B = N >= kThreads ? 1 : kThreads / N;
+    p.RN = (unsigned long long)R * (unsigned long long)N;
     p.is_ct = c.is_caretaker; p.calc_deg = c.calc_degradation; p.deg_mode = c.deg_mode; p.carry = c.carry_degradation_state;
     p.auto_reset = c.auto_reset; p.start_lo = c.start_lo; p.start_hi = c.start_hi; p.seed = c.seed;
     p.env_id_offset = env_id_offset;
@@ -1035,18 +1186,68 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     p.max_hn = (c.target_soc * c.init_battery_cap) / (c.evse_max_power * c.charging_eff);   // :50-51
     p.ev_rec = d_rec; p.step_row = d_rows; p.hdr = d_hdr;
 
-    // shared memory of the step kernel: env scratch + contributions + sums + rainflow index stack
-    const int slots = p.B * N;
-    const int cap = c.episode_steps + 2;
-    p.stack_u16 = cap > 255;
-    size_t sm = smem_envs_bytes(p.B) + (size_t)kNQ * slots * 8 + (size_t)kNSum * p.B * 8;
-    if (c.calc_degradation && c.deg_mode == FLEET_DEG_SEI) sm += (size_t)cap * kThreads * (p.stack_u16 ? 2 : 1);
-    sm = (sm + 15) & ~(size_t)15;
+    // exact division by eta_c through its reciprocal (Markstein): verify on the host that the two-FMA correction
+    // reproduces IEEE division for this constant; otherwise the kernel uses a true division.
+    p.eta_c_rcp = 1.0 / c.charging_eff;
+    p.eta_c_rcp_ok = 1;
+    {
+        unsigned long long x = 0x243F6A8885A308D3ull;
+        for (int it = 0; it < 2000000 && p.eta_c_rcp_ok; it++) {
+            x = x * 6364136223846793005ull + 1442695040888963407ull;
+            const double u = (double)(x >> 11) * (1.0 / 9007199254740992.0);      // [0,1)
+            const double a = (it & 1 ? -1.0 : 1.0) * ldexp(u + 0.5, (int)((x >> 3) % 40) - 30);
+            const double q0 = a * p.eta_c_rcp;
+            const double rem = fma(-q0, c.charging_eff, a);
+            const double q = fma(rem, p.eta_c_rcp, q0);
+            if (q != a / c.charging_eff) p.eta_c_rcp_ok = 0;
+        }
+    }
+    p.n_magic = (unsigned int)((0x100000000ull + (unsigned long long)N - 1) / (unsigned long long)N);
+    {
+        const unsigned long long Hh = (unsigned long long)(Ha + Hb > 0 ? Ha + Hb : 1);
+        p.h_magic = (unsigned int)((0x100000000ull + Hh - 1) / Hh);
+    }
+    p.off_contrib = (int)smem_envs_bytes(p.B);
+    p.off_obs = (int)smem_obs_offset(p.B, N);
+    p.bulk_ok = ((p.B * h->D) % 4 == 0) ? 1 : 0;
+
+    // shared memory of the step kernel: env scratch + contributions + sums + obs tile
+    size_t sm = smem_step_bytes(p.B, N, h->D);
     if ((int64_t)sm > (int64_t)h->max_smem_optin) {
         char buf[256];
-        snprintf(buf, sizeof buf, "step kernel needs %zu bytes of shared memory (episode of %d steps) but the device allows %d; "
-                 "long-episode global-memory rainflow stack is not implemented yet", sm, c.episode_steps, h->max_smem_optin);
+        snprintf(buf, sizeof buf, "step kernel needs %zu bytes of shared memory (N=%d, D=%d) but the device allows %d", sm, N,
+                 h->D, h->max_smem_optin);
         return fail(h, FLEET_E_INVALID, buf);
+    }
+    // post kernel: stack rings + one 32-bit record per rainflow cycle (at most L+1 cycles per vehicle)
+    const int cap = c.episode_steps + 2;
+    if (cap > 32767) return fail(h, FLEET_E_INVALID, "episodes longer than 32765 steps are not supported (15-bit sample indices)");
+    size_t smp = post_smem_bytes(cap);
+    if (!(c.calc_degradation && c.deg_mode == FLEET_DEG_SEI)) smp = 16;
+    if ((int64_t)smp > (int64_t)h->max_smem_optin) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "post kernel needs %zu bytes of shared memory for the rainflow cycle records of a %d-step episode "
+                 "but the device allows %d; spilling the records to global memory is not implemented yet", smp, c.episode_steps,
+                 h->max_smem_optin);
+        return fail(h, FLEET_E_INVALID, buf);
+    }
+    h->smem_post = smp;
+    h->num_sms = prop.multiProcessorCount;
+    h->need_post = (c.calc_degradation || c.auto_reset) ? 1 : 0;
+    {
+        int per_sm = 1;
+        CUDA_TRY(h, cudaFuncSetAttribute(pick_post(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post(h), kPostThreads, smp));
+        if (per_sm < 1) per_sm = 1;
+        const int64_t g = (int64_t)h->num_sms * per_sm;
+        h->grid_post = (int)(g < E ? g : E);
+    }
+    if (c.calc_degradation && c.deg_mode == FLEET_DEG_SEI) {
+        int sc = 64;
+        while (sc < cap) sc <<= 1;
+        p.scratch_cap = sc;
+        if ((rc = dev_alloc(h, &p.post_scratch_v, (size_t)h->grid_post * sc * kPostThreads, false))) return rc;
+        if ((rc = dev_alloc(h, &p.post_scratch_i, (size_t)h->grid_post * sc * kPostThreads, false))) return rc;
     }
     h->smem_step = sm;
     h->grid = (E + p.B - 1) / p.B;
@@ -1079,6 +1280,10 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     p.actions = actions_dev; p.obs = obs_dev; p.reward = reward_dev; p.done = done_dev; p.terminal_obs = terminal_obs_dev;
     pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
     h->launches++;
+    if (h->need_post) {   // daily degradation, then auto-reset, for the envs the step kernel put on the work list
+        pick_post(h)<<<h->grid_post, kPostThreads, h->smem_post, (cudaStream_t)stream>>>(p);
+        h->launches++;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, FLEET_E_CUDA, std::string("fleet_step launch: ") + cudaGetErrorString(e));
     return FLEET_OK;
@@ -1188,7 +1393,7 @@ int fleet_set_state(FleetHandle* h, int32_t field, const void* src_dev, void* st
 int fleet_get_stats(FleetHandle* h, double* dst_dev, void* stream) {
     if (!h || !dst_dev) return FLEET_E_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    reduce_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->p.stats, dst_dev);
+    reduce_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->p.stats, dst_dev, h->p.price_mult);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return FLEET_OK;

@@ -589,6 +589,7 @@ static void* step_range(void* arg) {
             if (j->reward64) j->reward64[i] = 0;
             if (j->cashflow) j->cashflow[i] = 0;
             if (j->done) j->done[i] = 1;
+            e->last_reward = 0; e->last_cashflow = 0; e->last_overload = 0; e->last_soc_viol = 0;
             continue;
         }
         double* target_before = scratch + N;      /* aux block uses the targets as of the observer call (:511) */

@@ -2,7 +2,9 @@
 
 Same fixtures and the same tolerances as tests/test_oracle_golden.py:
   bit-exact  : done, hours_left, target_soc, rainflow_length (cycle counts), soc, soc_deg, observation (float32)
-  rel 1e-12  : reward (device exp vs numpy exp in the two sigmoid penalties), cashflow (revenue factor regrouped)
+  rel 1e-11 / abs 1e-10 : reward (per-vehicle terms are added per vehicle first and then summed over the
+               fleet in car order — a deterministic re-association of the reference's sum — plus device exp vs numpy exp);
+  rel 1e-12  : cashflow (revenue factor regrouped)
   abs 1e-13  : SOH, l ; rel 1e-12 : fd_cyc   (device pow/exp vs numpy, summation order of the stress terms)
 """
 import numpy as np
@@ -59,7 +61,7 @@ def test_gpu_matches_reference(name):
     np.testing.assert_array_equal(o["target_soc"], r["target_soc"])
     np.testing.assert_array_equal(o["soc"], r["soc"])
     np.testing.assert_array_equal(o["soc_deg"], r["soc_deg"])
-    np.testing.assert_allclose(o["reward"], r["reward"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(o["reward"], r["reward"], rtol=1e-11, atol=1e-10)
     np.testing.assert_allclose(o["cashflow"], r["cashflow"], rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(o["soh"], r["soh"], rtol=0, atol=1e-13)
     if "rf_len" in r:

@@ -2,7 +2,7 @@
 
 Bit-exact (asserted with array_equal): done, time index, hours_left, soc, soc_deg, target flags, rainflow cycle
 counts / rainflow_length, observations (float32), terminal observations, start indices drawn by the device RNG.
-Tolerance: reward rel 1e-12 (exp), cashflow rel 1e-12 (regrouped revenue factor), SOH abs 1e-13, fd_cyc rel 1e-11.
+Tolerance: reward rel 1e-11 / abs 1e-10 (deterministic re-association of the per-env sum, exp), cashflow rel 1e-12 (regrouped revenue factor), SOH abs 1e-13, fd_cyc rel 1e-11.
 """
 import numpy as np
 import pytest
@@ -79,7 +79,7 @@ def test_gpu_vs_oracle(name):
         np.testing.assert_array_equal(g_done, o_done, err_msg=f"done step {s}")
         for k in exact:
             np.testing.assert_array_equal(gpu.get(k).cpu().numpy(), orc.get(k), err_msg=f"{k} step {s}")
-        np.testing.assert_allclose(gpu.get("reward64").cpu().numpy(), o_rew, rtol=1e-12, atol=1e-12, err_msg=f"reward step {s}")
+        np.testing.assert_allclose(gpu.get("reward64").cpu().numpy(), o_rew, rtol=1e-11, atol=1e-10, err_msg=f"reward step {s}")
         np.testing.assert_allclose(gpu.get("cashflow").cpu().numpy(), o_cash, rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(rew.cpu().numpy(), o_rew.astype(np.float32), rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(gpu.get("soh").cpu().numpy(), orc.get("soh"), rtol=0, atol=1e-13, err_msg=f"soh step {s}")
