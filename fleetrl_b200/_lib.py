@@ -47,7 +47,7 @@ def load_library(path: str = LIB_PATH):
         getattr(L, f).argtypes = [vp]
     L.fleet_reset.argtypes = [vp, vp, vp, vp, vp]
     L.fleet_step.argtypes = [vp, vp, vp, vp, vp, vp, vp]
-    L.fleet_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.fleet_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.fleet_set_next_start.argtypes = [vp, vp]
     L.fleet_get_state.argtypes = [vp, i32, vp, vp]
     L.fleet_set_state.argtypes = [vp, i32, vp, vp]
@@ -147,15 +147,17 @@ class FleetStepHandle:
         if rc != 0:
             self._check(rc, "fleet_step")
 
-    def step_host(self, actions, obs, reward, done):
+    def step_host(self, actions, obs, reward, done, terminal_obs=None):
         """NumPy / pinned-host call: H2D copy, step, D2H copies, stream sync — all inside the library."""
+        self._chk_tensor(terminal_obs, (self.E, self.D), torch.float32, "terminal_obs")
         for a, shape, dt, nm in ((actions, (self.E, self.N), np.float32, "actions"), (obs, (self.E, self.D), np.float32, "obs"),
                                  (reward, (self.E,), np.float32, "reward"), (done, (self.E,), np.uint8, "done")):
             if a is not None and (a.dtype != dt or tuple(a.shape) != shape or not a.flags.c_contiguous):
                 raise FleetStepError(f"{nm}: expected C-contiguous {dt} array of shape {shape}")
         self._check(self.lib.fleet_step_host(self._h, actions.ctypes.data, None if obs is None else obs.ctypes.data,
                                              None if reward is None else reward.ctypes.data,
-                                             None if done is None else done.ctypes.data, _stream_ptr(self.device)),
+                                             None if done is None else done.ctypes.data, _dptr(terminal_obs),
+                                             _stream_ptr(self.device)),
                     "fleet_step_host")
 
     def set_next_start(self, next_start):

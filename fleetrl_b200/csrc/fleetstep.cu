@@ -1290,7 +1290,7 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
 }
 
 int fleet_step_host(FleetHandle* h, const float* actions_host, float* obs_host, float* reward_host, uint8_t* done_host,
-                    void* stream) {
+                    float* terminal_obs_dev, void* stream) {
     if (!h) return FLEET_E_INVALID;
     if (!actions_host) return fail(h, FLEET_E_INVALID, "actions_host is NULL");
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -1304,7 +1304,7 @@ int fleet_step_host(FleetHandle* h, const float* actions_host, float* obs_host, 
         if ((rc = dev_alloc(h, &h->h_done_dev, (size_t)h->E, false))) return rc;
     }
     CUDA_TRY(h, cudaMemcpyAsync(h->h_actions_dev, actions_host, EN * 4, cudaMemcpyHostToDevice, s));
-    if ((rc = fleet_step(h, h->h_actions_dev, h->h_obs_dev, h->h_reward_dev, h->h_done_dev, nullptr, stream))) return rc;
+    if ((rc = fleet_step(h, h->h_actions_dev, h->h_obs_dev, h->h_reward_dev, h->h_done_dev, terminal_obs_dev, stream))) return rc;
     if (obs_host) CUDA_TRY(h, cudaMemcpyAsync(obs_host, h->h_obs_dev, ED * 4, cudaMemcpyDeviceToHost, s));
     if (reward_host) CUDA_TRY(h, cudaMemcpyAsync(reward_host, h->h_reward_dev, (size_t)h->E * 4, cudaMemcpyDeviceToHost, s));
     if (done_host) CUDA_TRY(h, cudaMemcpyAsync(done_host, h->h_done_dev, (size_t)h->E, cudaMemcpyDeviceToHost, s));

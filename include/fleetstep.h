@@ -188,9 +188,11 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
                float* terminal_obs_dev, void* stream);
 
 /* Same step with HOST buffers (pinned or pageable): copies actions up, steps, copies obs/reward/done back and
- * synchronises the stream.  This is the call an SB3-style NumPy caller makes; bench.py times it as "e2e". */
+ * synchronises the stream.  This is the call an SB3-style NumPy caller makes; bench.py times it as "e2e".
+ * terminal_obs_dev (optional, DEVICE float32 [E][D]) receives the terminal rows of finished envs as in fleet_step;
+ * the caller fetches only the rows it needs (finished envs are rare). */
 int fleet_step_host(FleetHandle* h, const float* actions_host, float* obs_host, float* reward_host,
-                    uint8_t* done_host, void* stream);
+                    uint8_t* done_host, float* terminal_obs_dev, void* stream);
 
 /* Start indices consumed by the next auto-resets instead of the RNG (parity runs inject them the way the
  * reference harness replaces env.time_picker).  NULL restores the RNG. The array must stay

@@ -1,0 +1,93 @@
+"""The SB3-shaped FleetVecEnv and the gym-shaped FleetEnv on the GPU, checked against the oracle through the
+public API (synthetic fleet from the product's own generator + table builder)."""
+import numpy as np
+import pytest
+import torch
+
+from fleetrl_b200.config import default_config
+from fleetrl_b200.schedule import generate_schedule, synthetic_series
+from fleetrl_b200.tables import FleetInputs, build_fleet
+from oracle.oracle import OracleFleet
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(use_case="lmd", n=6):
+    sched = generate_schedule(use_case, n, start="2020-01-01 00:00", end="2020-03-31 23:59", seed=11)
+    price, tariff, load, pv = synthetic_series(start="2020-01-01 00:00", end="2020-03-31 23:59")
+    return FleetInputs(sched, price, tariff, load, pv)
+
+
+@pytest.mark.parametrize("output", ["torch", "numpy"])
+def test_vec_env_matches_oracle(output):
+    from fleetrl_b200 import FleetVecEnv
+    cfg = default_config("lmd", time_picker="random", end_cutoff=10)
+    inputs = _inputs()
+    E = 48
+    env = FleetVecEnv(cfg, E, inputs=inputs, output=output, env_id_offset=77, seed=3)
+    orc = OracleFleet(env.built.consts, env.built.tables, E, env_id_offset=77)
+    assert env.observation_space.shape == (env.obs_dim,) and env.action_space.shape == (6,)
+    obs = env.reset()
+    o_obs = orc.reset()
+    np.testing.assert_array_equal(obs.cpu().numpy() if output == "torch" else obs, o_obs)
+    rng = np.random.default_rng(0)
+    seen_done = 0
+    for s in range(200):
+        a = rng.uniform(-1, 1, (E, 6)).astype(np.float32)
+        obs, rew, done, infos = env.step(a if output == "numpy" else torch.from_numpy(a).to(env.device))
+        o_obs, o_rew, _, o_done, o_term = orc.step(a, want_terminal=True)
+        g_obs = obs.cpu().numpy() if output == "torch" else obs
+        g_done = done.cpu().numpy() if output == "torch" else done
+        g_rew = rew.cpu().numpy() if output == "torch" else rew
+        np.testing.assert_array_equal(g_done, o_done.astype(bool))
+        np.testing.assert_array_equal(g_obs, o_obs)
+        np.testing.assert_allclose(g_rew, o_rew.astype(np.float32), rtol=1e-6, atol=1e-6)
+        assert len(infos) == E
+        for i in np.nonzero(o_done)[0]:
+            info = infos[int(i)]
+            t = info["terminal_observation"]
+            np.testing.assert_array_equal(t.cpu().numpy() if output == "torch" else t, o_term[i])
+            assert info["TimeLimit.truncated"] is False and info["episode"]["l"] == 96
+            np.testing.assert_allclose(info["episode"]["r"], orc.get("last_ep_return")[i], rtol=1e-11)
+            seen_done += 1
+        if not o_done.any():
+            assert infos[0] == {}
+    assert seen_done >= E
+    # env_method surface
+    assert env.env_method("is_done", indices=[0]) == [bool(o_done[0])]
+    t = env.env_method("get_time", indices=0)[0]
+    assert t == env.built.dates[orc.get("time_idx")[0]]
+    df = env.env_method("get_dist_factor", indices=[1])[0]
+    assert df.shape == (6,)
+    assert env.env_is_wrapped(None) == [False] * E
+    st, ost = env.stats(), orc.stats()
+    for k in ost:
+        np.testing.assert_allclose(st[k], ost[k], rtol=1e-9, atol=1e-9, err_msg=k)
+    env.close()
+
+
+def test_fleet_env_gym_api():
+    from fleetrl_b200 import FleetEnv
+    cfg = default_config("ct", time_picker="static", episode_length=48)
+    inputs = _inputs("ct", 4)
+    env = FleetEnv(cfg, inputs=inputs)
+    built = build_fleet(cfg, inputs, auto_reset=False)
+    orc = OracleFleet(built.consts, built.tables, 1)
+    obs, info = env.reset()
+    assert info == {} and obs.dtype == np.float32 and obs.shape == env.observation_space.shape
+    t0 = built.start_ranges["static"][0]
+    np.testing.assert_array_equal(obs, orc.reset(start_idx=[t0])[0])
+    assert env.get_time() == built.dates[t0] == env.get_start_time()
+    rng = np.random.default_rng(1)
+    for s in range(192):
+        a = rng.uniform(-1, 1, 4).astype(np.float32)
+        obs, r, done, trunc, info = env.step(a)
+        o_obs, o_r, _, o_d = orc.step(a[None, :])
+        np.testing.assert_array_equal(obs, o_obs[0])
+        assert isinstance(r, float) and trunc is False and info == {}
+        np.testing.assert_allclose(r, o_r[0], rtol=1e-11, atol=1e-10)
+        assert done == bool(o_d[0])
+    assert done and env.is_done()
+    with pytest.raises(TypeError):
+        env.step(np.array([np.nan, 0, 0, 0], dtype=np.float32))
+    env.close()

@@ -1,0 +1,123 @@
+"""CPU-only tests of the host side: config mirror, spaces, lazy infos, sharding, the schedule generator + table
+builder invariants, and that the C-ABI library loads and exports every symbol include/fleetstep.h declares."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from fleetrl_b200 import config as cfgmod
+from fleetrl_b200._abi import FleetConsts
+from fleetrl_b200.dist import shard_range
+from fleetrl_b200.schedule import generate_schedule, synthetic_series
+from fleetrl_b200.spaces import action_box, observation_box
+from fleetrl_b200.tables import FleetInputs, build_fleet
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    """Every function declared in include/fleetstep.h is exported by the built library (no compute calls)."""
+    import __graft_entry__ as g
+    g.build()
+    hdr = open(os.path.join(ROOT, "include", "fleetstep.h")).read()
+    names = set(re.findall(r"\b(fleet_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 19
+    lib = ctypes.CDLL(os.path.join(ROOT, "fleetrl_b200", "libfleetstep.so"))
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} is declared in fleetstep.h but not exported"
+    lib.fleet_abi_version.restype = ctypes.c_int
+    assert lib.fleet_abi_version() == 1
+
+
+def test_consts_struct_matches_header_size():
+    # 21 int32 (+pad) + uint64 + 31 doubles, laid out like the C struct
+    assert ctypes.sizeof(FleetConsts) == 80 + 8 + 8 * 31
+
+
+def test_config_resolution_order():
+    cfg = cfgmod.default_config("ct", spot_markup=0, spot_mul=1, feed_in_ded=0, target_soc=0.8,
+                                max_batt_cap_in_all_use_cases=60, ignore_invalid_penalty=True)
+    rc = cfgmod.resolve(cfg)
+    assert rc.ev.init_battery_cap == 16.7 and rc.ev.fixed_markup == 0 and rc.ev.variable_multiplier == 1
+    assert rc.ev.feed_in_deduction == 0 and rc.ev.target_soc == 0.8
+    assert rc.score.price_multiplier == 3.33 * (60 / 16.7)          # fleet_environment.py:194
+    assert rc.score.penalty_invalid_action == 0
+    co = cfgmod.company_for("ct", cfg, max_load=100.0, num_cars=20)
+    assert co.evse_max_power == 4.6 and co.grid_connection == max(110.00000000000001, 100 + 0.5 * 20 * 4.6)
+    assert cfgmod.company_for("ut", cfg, 50.0, 5).grid_connection == 1000
+
+
+def test_config_errors():
+    cfg = cfgmod.default_config("lmd")
+    bad = dict(cfg); del bad["target_soc"]
+    with pytest.raises(KeyError):
+        cfgmod.resolve(bad)
+    with pytest.raises(NotImplementedError):
+        cfgmod.resolve(dict(cfg, include_price=False))
+    with pytest.raises(NotImplementedError):
+        cfgmod.resolve(dict(cfg, real_time=True))
+    with pytest.raises(TypeError):
+        cfgmod.resolve(dict(cfg, use_case="bus"))
+    with pytest.raises(AssertionError):
+        cfgmod.read_config(3.14)
+
+
+def test_spaces():
+    ob = observation_box(388, normalized=False)
+    assert ob.shape == (388,) and ob.dtype == np.float32 and np.isinf(ob.low).all()
+    ob = observation_box(45, normalized=True)
+    assert ob.low.min() == 0 and ob.high.max() == 1
+    ab = action_box(50)
+    assert ab.shape == (50,) and ab.low.min() == -1 and ab.high.max() == 1
+
+
+def test_shard_range_covers_everything():
+    for total, world in [(65536, 8), (1048576, 8), (10, 4), (3, 8), (0, 2)]:
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 4, 4)
+
+
+def test_lazy_infos():
+    from fleetrl_b200.vec_env import LazyInfos
+    term = np.arange(6, dtype=np.float32).reshape(2, 3)
+    infos = LazyInfos(5, [1, 4], term, np.array([-3.0, 2.5]), 96)
+    assert len(infos) == 5 and infos[0] == {} and infos[-1]["episode"]["r"] == 2.5
+    assert np.array_equal(infos[1]["terminal_observation"], term[0]) and infos[1]["TimeLimit.truncated"] is False
+    assert infos[4]["episode"]["l"] == 96 and [bool(i) for i in infos] == [False, True, False, False, True]
+    with pytest.raises(IndexError):
+        infos[5]
+
+
+@pytest.mark.parametrize("use_case", ["lmd", "ut", "ct"])
+def test_generator_and_builder_invariants(use_case):
+    sched = generate_schedule(use_case, 3, start="2020-01-01 00:00", end="2020-02-29 23:59", seed=5)
+    assert list(sched.columns) == ["date", "Distance_km", "Consumption_kWh", "Location", "ChargingStation", "ID", "PowerRating_kW"]
+    price, tariff, load, pv = synthetic_series(start="2020-01-01 00:00", end="2020-02-29 23:59")
+    b = build_fleet(cfgmod.default_config(use_case, time_picker="random", end_cutoff=10), FleetInputs(sched, price, tariff, load, pv))
+    tb, c = b.tables, b.consts
+    N, T = tb["there"].shape
+    assert N == 3 and T == 60 * 96 and c.table_len == T and c.num_evs == 3
+    there, tl, sr = tb["there"], tb["time_left"], tb["soc_on_return"]
+    assert ((there == 0) | (there == 1)).all()
+    assert (tl[there == 0] == 0).all() and (sr[there == 0] == 0).all()
+    # while a vehicle stays plugged in, time_left counts down by exactly dt per step
+    stay = (there[:, :-1] == 1) & (there[:, 1:] == 1) & (tl[:, 1:] > 0)
+    assert np.array_equal(tl[:, :-1][stay] - c.dt, tl[:, 1:][stay])
+    # the row before a departure shows exactly one step left
+    dep = (there[:, :-1] == 1) & (there[:, 1:] == 0)
+    assert (tl[:, :-1][dep] == c.dt).all()
+    assert sr.max() <= c.target_soc + 1e-12 and c.start_lo == 0 and 0 < c.start_hi < T
+    if use_case == "lmd":   # no Sunday operation
+        sunday = np.array([d.astype("datetime64[D]").astype(object).weekday() == 6 for d in b.dates])
+        assert (there[:, sunday] == 1).all()
+    # reward curves: monthly means equal the global mean (shape_price_reward)
+    prc = tb["price_reward_curve"]
+    jan = prc[: 31 * 96]
+    assert abs(jan.mean() - prc.mean()) < 1e-9
