@@ -1,0 +1,82 @@
+"""Full-size checks at BASELINE.json configs[1] (65,536 envs x 50 EVs, SEI degradation) through the C ABI.
+
+The oracle cannot step 3.3 M vehicles for a day in test time, so at full size the checks are:
+  * a 1,024-env SLICE of the full batch is compared with the oracle run on the same global env ids (identical start
+    draws, same actions): bit-exact state / observations, reward within tolerance;
+  * sharding invariance: the same global env ids stepped by a second handle with an env_id_offset reproduce the
+    slice of the big handle bit for bit (what makes 1/2/4/8-GPU runs comparable);
+  * size-independent invariants over ALL envs: time index advances by one, hours_left is an exact multiple of dt,
+    SOC stays in [0, 1] up to rounding, presence-consistent hours_left, statistics add up.
+"""
+import numpy as np
+import pytest
+import torch
+
+from fleetrl_b200.config import default_config
+from fleetrl_b200.schedule import generate_schedule, synthetic_series
+from fleetrl_b200.tables import FleetInputs, build_fleet
+from oracle.oracle import OracleFleet
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cfg2_full_size_slice_and_invariants():
+    from fleetrl_b200._lib import FleetStepHandle
+    E, N, S0, SN, STEPS = 65536, 50, 30000, 1024, 120
+    sched = generate_schedule("lmd", N, seed=42)
+    price, tariff, load, pv = synthetic_series(seed=7)
+    built = build_fleet(default_config("lmd", seed=0), FleetInputs(sched, price, tariff, load, pv), auto_reset=True,
+                        carry_degradation_state=True, seed=0, time_picker="random")
+    c, tb = built.consts, built.tables
+    big = FleetStepHandle(c, tb, E, device=0, env_id_offset=0)
+    small = FleetStepHandle(c, tb, SN, device=0, env_id_offset=S0)
+    orc = OracleFleet(c, tb, SN, env_id_offset=S0, threads=8)
+    dev = big.device
+    D = big.D
+    assert D == 388
+    obs = torch.zeros((E, D), dtype=torch.float32, device=dev)
+    rew = torch.zeros(E, dtype=torch.float32, device=dev)
+    done = torch.zeros(E, dtype=torch.uint8, device=dev)
+    obs_s = torch.zeros((SN, D), dtype=torch.float32, device=dev)
+    big.reset(obs=obs); small.reset(obs=obs_s)
+    o_obs = orc.reset()
+    sl = slice(S0, S0 + SN)
+    np.testing.assert_array_equal(obs[sl].cpu().numpy(), o_obs)
+    assert torch.equal(obs[sl], obs_s)
+    gen = torch.Generator(device=dev); gen.manual_seed(5)
+    t_prev = big.get("time_idx").clone()
+    n_done = 0
+    for s in range(STEPS):
+        a = torch.empty((E, N), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=gen)
+        if s % 9 == 0:
+            a[:, ::3] = 0.0
+        big.step(a, obs, rew, done)
+        small.step(a[sl].contiguous(), obs_s)
+        o_obs, o_rew, _, o_done = orc.step(a[sl].cpu().numpy())
+        # slice vs oracle
+        np.testing.assert_array_equal(done[sl].cpu().numpy(), o_done, err_msg=f"done step {s}")
+        np.testing.assert_array_equal(obs[sl].cpu().numpy(), o_obs, err_msg=f"obs step {s}")
+        np.testing.assert_array_equal(big.get("soc")[sl].cpu().numpy(), orc.get("soc"), err_msg=f"soc step {s}")
+        np.testing.assert_array_equal(big.get("rf_len")[sl].cpu().numpy(), orc.get("rf_len"), err_msg=f"rf_len step {s}")
+        np.testing.assert_allclose(big.get("reward64")[sl].cpu().numpy(), o_rew, rtol=1e-11, atol=1e-10)
+        np.testing.assert_allclose(big.get("soh")[sl].cpu().numpy(), orc.get("soh"), rtol=0, atol=1e-13)
+        # sharding invariance
+        assert torch.equal(obs[sl], obs_s), f"shard obs differs at step {s}"
+        assert torch.equal(big.get("soc")[sl], small.get("soc"))
+        # invariants over all envs
+        t_now = big.get("time_idx")
+        d = done.bool()
+        assert torch.equal(t_now[~d], t_prev[~d] + 1)
+        t_prev = t_now.clone()
+        n_done += int(d.sum().item())
+        if s % 20 == 0:
+            hl = big.get("hours_left")
+            assert torch.equal(hl, torch.round(hl * 4) / 4) and float(hl.min()) >= 0
+            soc = big.get("soc")
+            assert float(soc.min()) > -1e-9 and float(soc.max()) < 1 + 1e-9
+            assert torch.isfinite(obs).all()
+    st = big.stats()
+    assert st["steps"] == E * STEPS and st["episodes"] == n_done
+    assert big.check_errors() == 0
+    for h in (big, small):
+        h.close()
