@@ -28,6 +28,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -77,6 +78,12 @@ struct __align__(16) StepRow {
 };
 static_assert(sizeof(StepRow) == 64, "StepRow must be 64 bytes");
 
+struct TmaLayout {
+    int act, soc, hl, soh, hist, rec, hdr, row, in_bytes;      // one input stage
+    int o_soc, o_hl, o_hist, o_obs, out_bytes;                 // one output buffer
+    int in0, out0, contrib, contrib_bytes, sums, bars, total;  // per CTA
+};
+
 struct StepParams {
     // sizes
     int E, N, T, R, L, D, Ha, Hb, hdr_stride, B;
@@ -85,12 +92,14 @@ struct StepParams {
     unsigned int h_magic;     // same for the header length Ha+Hb
     int off_contrib, off_obs; // byte offsets of the contribution arrays / obs tile in dynamic shared memory
     // flags
-    int is_ct, calc_deg, deg_mode, carry, auto_reset, bulk_ok, eta_c_rcp_ok;
+    int is_ct, calc_deg, deg_mode, carry, auto_reset, bulk_ok;
+    int Bt;                   // envs per tile of the TMA kernel (0 = TMA path not applicable)
+    TmaLayout tl;             // shared-memory layout of the TMA kernel
     int start_lo, start_hi;
     unsigned long long seed;
     long long env_id_offset;
     // constants
-    double dt, P, eta_c, eta_c_rcp, eta_d, mult, cap0, target, target_lunch, eps, def_soc, min_lax;
+    double dt, P, eta_c, eta_d, mult, cap0, target, target_lunch, eps, def_soc, min_lax;
     double pen_inv, pen_oc, clip_oc, pen_ovl, full_reward, evse, grid, init_soh, lc_batt_cap, hn_den, price_mult;
     double temperature, max_tl, max_soc, max_hn;
     float dt_f;
@@ -156,6 +165,31 @@ __device__ __forceinline__ int draw_start(unsigned long long seed, int start_lo,
     return start_lo + (int)(h % span);
 }
 
+
+// L2 residency: the time-indexed tables and the per-env time index are re-read every step by (other) envs, the
+// [E][N] state streams through once per step.  Table / env4 accesses carry an evict_last policy, streaming state
+// uses evict-first (ld.global.cs / st.global.cs).
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int4 ld_keep_v4(const void* ptr, uint64_t pol) {
+    int4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_keep_f32(const float* ptr, uint64_t pol) {
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_keep_v4(void* ptr, int4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ EvRec load_rec(const EvRec* ptr) {
     // two 128-bit read-only loads of one 32-byte sector (tables keep the default L2 policy; streaming state uses
     // evict-first loads/stores so the tables stay resident)
@@ -168,6 +202,19 @@ __device__ __forceinline__ EvRec load_rec(const EvRec* ptr) {
     r.there_prev = (uint8_t)((v.w >> 8) & 0xff);
     r.pad = 0;
     r.tt = w.x; r.cl = w.y; r.hn = w.z; r.lax = w.w;
+    return r;
+}
+
+__device__ __forceinline__ EvRec load_rec_keep(const EvRec* ptr, uint64_t pol) {
+    const int4 v = ld_keep_v4(ptr, pol);
+    const int4 w = ld_keep_v4(reinterpret_cast<const int4*>(ptr) + 1, pol);
+    EvRec r;
+    r.sr = __hiloint2double(v.y, v.x);
+    r.tl = __int_as_float(v.z);
+    r.there = (uint8_t)(v.w & 0xff);
+    r.there_prev = (uint8_t)((v.w >> 8) & 0xff);
+    r.pad = 0;
+    r.tt = __int_as_float(w.x); r.cl = __int_as_float(w.y); r.hn = __int_as_float(w.z); r.lax = __int_as_float(w.w);
     return r;
 }
 
@@ -454,7 +501,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
     const int cstride = B * N;  // contrib[q][slot]
     double* sums = contrib + kNQ * cstride;
     float* obs_tile = reinterpret_cast<float*>(smem_raw + p.off_obs);
-    __shared__ int s_any;       // bit1: some env of the tile finished and auto-resets (its row goes to terminal_obs)
 
     const int tid = threadIdx.x;
     const int e0 = blockIdx.x * B;
@@ -463,13 +509,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
     const int npass = (nslots + kThreads - 1) / kThreads;   // 1 unless N > kThreads
     const int H = p.Ha + p.Hb;
 
-    if (tid == 0) s_any = 0;
-    __syncthreads();
+    const uint64_t keep = l2_evict_last_policy();
+    int my_any = 0;             // bit1: this env finished and auto-resets (its row goes to terminal_obs)
 
     // ---- P0: one thread per env: time index, per-time factors, flags
     if (tid < nb) {
         const int e = e0 + tid;
-        const int4 ev = p.env4[e];
+        const int4 ev = ld_keep_v4(p.env4 + e, keep);
         EnvS& es = envs[tid];
         es.t = ev.x; es.t_start = ev.y; es.ep_count = ev.z;
         const int t_fin = ev.y + p.L;
@@ -477,12 +523,15 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
         if (!p.auto_reset && ev.x >= t_fin) fl |= EF_FROZEN;   // episode over and not reset by the caller
         const int t = min(ev.x, p.T - 2);
         const StepRow* r = p.step_row + t;
-        const double2 ra = __ldg(reinterpret_cast<const double2*>(r));
-        const double2 rb = __ldg(reinterpret_cast<const double2*>(r) + 1);
-        const double2 r1 = __ldg(reinterpret_cast<const double2*>(r) + 2);
-        const double2 r2 = __ldg(reinterpret_cast<const double2*>(r) + 3);
-        es.S = ra.x; es.F_cr = ra.y; es.F_dr = rb.x; es.Rfac = rb.y; es.pv_share = r1.x; es.gml = r1.y; es.pvv = r2.x;
-        const uint32_t fn = (uint32_t)(__double_as_longlong(r2.y) >> 32);  // flags_next (little endian: second u32)
+        const int4 ra = ld_keep_v4(reinterpret_cast<const int4*>(r), keep);
+        const int4 rb = ld_keep_v4(reinterpret_cast<const int4*>(r) + 1, keep);
+        const int4 r1 = ld_keep_v4(reinterpret_cast<const int4*>(r) + 2, keep);
+        const int4 r2 = ld_keep_v4(reinterpret_cast<const int4*>(r) + 3, keep);
+        es.S = __hiloint2double(ra.y, ra.x); es.F_cr = __hiloint2double(ra.w, ra.z);
+        es.F_dr = __hiloint2double(rb.y, rb.x); es.Rfac = __hiloint2double(rb.w, rb.z);
+        es.pv_share = __hiloint2double(r1.y, r1.x); es.gml = __hiloint2double(r1.w, r1.z);
+        es.pvv = __hiloint2double(r2.y, r2.x);
+        const uint32_t fn = (uint32_t)r2.w;                                  // flags_next
         if (!(fl & EF_FROZEN)) {
             if (ev.x + 1 == t_fin) fl |= EF_DONE;
             if ((fn & TF_TRIGGER) && p.calc_deg) fl |= EF_TRIGGER;
@@ -494,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
         // post kernel) and the last observation of the finished one in infos["terminal_observation"].
         if (fl & EF_RESET) es.obs_dst = p.terminal_obs ? p.terminal_obs + (size_t)e * D : nullptr;
         else es.obs_dst = p.obs ? p.obs + (size_t)e * D : nullptr;
-        if (fl & EF_RESET) atomicOr(&s_any, 2);
+        if (fl & EF_RESET) my_any = 2;
     }
 
     const bool have_flips = (*p.n_flips != 0);
@@ -516,7 +565,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
             n = j - b * N;
             const int e = e0 + b;
             i = (size_t)e0 * N + j;
-            const int4 ev = p.env4[e];
+            const int4 ev = ld_keep_v4(p.env4 + e, keep);
             t = ev.x; k = ev.x - ev.y;
             a32 = __ldcs(p.actions + i);
             soc = __ldcs(p.soc + i);
@@ -525,19 +574,16 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
             hrow = (size_t)e * p.RN + (unsigned)((p.calc_deg ? k : (k & 1)) * N + n);
             sdeg = __ldcs(p.hist + hrow);
             const int tr = (!p.auto_reset && k >= p.L) ? min(t, p.T - 1) : min(t + 1, p.T - 1);   // frozen: row t
-            rec = load_rec(&p.ev_rec[(size_t)tr * N + n]);
+            rec = load_rec_keep(&p.ev_rec[(size_t)tr * N + n], keep);
         }
-        if (pass == 0) {
-            __syncthreads();
-            any = s_any;
-        }
+        if (pass == 0) any = __syncthreads_or(my_any) ? 2 : 0;   // returns a predicate, not the OR-ed value
         // time-only part of the observation: host-precomputed float32 row per time index, one element per thread
         float hv = 0.f; int hdst = -1;
         if (pass == 0 && tid < nb * H) {
             const int bb = (H == 1) ? tid : (int)__umulhi((unsigned)tid, p.h_magic), q = tid - bb * H;
             const EnvS& eh = envs[bb];
             const int th = (eh.flags & EF_FROZEN) ? min(eh.t, p.T - 1) : min(eh.t + 1, p.T - 1);
-            hv = __ldg(p.hdr + (size_t)th * p.hdr_stride + q);
+            hv = ld_keep_f32(p.hdr + (size_t)th * p.hdr_stride + q, keep);
             hdst = bb * D + (q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha));
         }
 
@@ -564,15 +610,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
                     }
                     double en = 0;
                     if (there == 1) {
-                        double q;                                               // dem / eta_c, correctly rounded
-                        if (p.eta_c_rcp_ok) {
-                            const double q0 = dem * p.eta_c_rcp;                // Markstein: r = RN(1/b); q0 = RN(a r);
-                            const double rem = fma(-q0, p.eta_c, dem);          // rem = a - q0 b (exact);
-                            q = fma(rem, p.eta_c_rcp, q0);                      // q = RN(q0 + rem r)
-                        } else {
-                            q = dem / p.eta_c;
-                        }
-                        en = fmin(q, req);
+                        en = fmin(dem / p.eta_c, req);                          // IEEE divide: SOC must be bit-exact
                     } else if (fabs(a) > 0.05) {
                         c_inv = p.pen_inv * (a * a);
                     }
@@ -644,6 +682,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
         obs_tile[bb * D + (q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha))] =
             __ldg(p.hdr + (size_t)th * p.hdr_stride + q);
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // writers: generic-proxy stores -> async proxy
     __syncthreads();
 
     // ---- observation tile -> HBM: one TMA bulk store per CTA when every row goes to obs[e0 .. e0+nb)
@@ -703,7 +742,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
                 p.env_f64[(size_t)EF_LAST_EP_RETURN * p.E + e] = ep_ret;
             }
             p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
-            p.env4[e] = make_int4(es.t + 1, es.t_start, es.ep_count, 0);
+            st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, 0), keep);
             const int wf = ((es.flags & EF_TRIGGER) ? WL_TRIGGER : 0) | ((es.flags & EF_RESET) ? WL_RESET : 0);
             if (wf) {   // the post kernel evaluates the degradation first and resets afterwards, like the reference
                 const int slot = atomicAdd(p.wl_count, 1);
@@ -718,6 +757,417 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
         if (p.done) p.done[e] = (uint8_t)done;
     }
     if (use_bulk && tid == 0) bulk_store_wait_read();   // the tile must stay valid until the bulk copy has read it
+}
+
+// ------------------------------------------------------------------------------------- persistent TMA step kernel
+// Same arithmetic as fleet_step_kernel, restructured for latency hiding and fewer per-thread instructions:
+//  * persistent CTAs (grid = #SMs x resident CTAs) loop over tiles of Bt consecutive envs;
+//  * WARP SPECIALISED: kWsCompute compute warps + one manager warp, no CTA-wide barrier in the loop.
+//    - the manager warp brings every input of a tile into a shared-memory STAGE with bulk-async copies
+//      (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP): the four contiguous [Bt*N] runs of actions / soc /
+//      hours_left / soh, and per env the previous history row, the schedule-record row ev_rec[t+1], the observation
+//      header row hdr[t+1] and step_row[t].  kWsStages stages are in flight, so the loads of the next tile overlap
+//      the arithmetic of the current one.
+//    - compute threads (one per (env, EV) slot) wait on the stage's `full` mbarrier, read their inputs from shared
+//      memory, update soc / hours_left / the history row IN PLACE in the stage, build the observation rows next to
+//      it, leave their per-vehicle reward/cashflow terms in a double-buffered contribution array and arrive on the
+//      stage's `done` mbarrier.
+//    - the manager warp, one tile behind, issues bulk stores for everything (state runs, history rows, one
+//      observation row per env to obs or — for a finished env — to terminal_obs), refills the stage as soon as the
+//      stores have read it, then does the per-env sequential sums and the env-level finalisation (reward, overload
+//      sigmoid, done, statistics, work list) while the compute warps are already on the next tile.
+// Selected by fleet_step when auto_reset is on, N is even (16-byte history rows), D % 4 == 0 and 7 <= N <= 224;
+// otherwise the generic kernel above runs.  tests/ exercise both.
+constexpr int kWsComputeWarps = 7;
+constexpr int kWsCompute = kWsComputeWarps * 32;       // 224 compute threads
+constexpr int kWsThreads = kWsCompute + 32;            // + manager warp
+constexpr int kWsStages = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait suspends the thread for a hardware-defined time before returning false (a __nanosleep back-off here
+    // was measured to be 2.4x slower: the hand-offs are on the critical path)
+    while (!mbar_try_wait(bar, parity)) { }
+}
+__device__ __forceinline__ void tma_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
+// byte offsets (all multiples of 16): input stage, output buffer, per-CTA arrays.  Computed once on the host and
+// passed in StepParams so that no thread spends instructions on it.
+inline TmaLayout tma_layout(int Bt, int N, int D, int hdr_stride) {
+    TmaLayout L;
+    const int bn = Bt * N;
+    auto a16 = [](size_t x) { return (int)((x + 15) & ~(size_t)15); };
+    int o = 0;
+    L.soc = o; o += a16((size_t)bn * 8);
+    L.soh = o; o += a16((size_t)bn * 8);
+    L.hist = o; o += a16((size_t)bn * 8);
+    L.rec = o; o += bn * 32;
+    L.row = o; o += Bt * 64;
+    L.act = o; o += a16((size_t)bn * 4);
+    L.hl = o; o += a16((size_t)bn * 4);
+    L.hdr = o; o += Bt * hdr_stride * 4;
+    L.in_bytes = a16((size_t)o);
+    o = 0;
+    L.o_soc = o; o += a16((size_t)bn * 8);
+    L.o_hist = o; o += a16((size_t)bn * 8);
+    L.o_hl = o; o += a16((size_t)bn * 4);
+    L.o_obs = o; o += a16((size_t)Bt * D * 4);
+    L.out_bytes = a16((size_t)o);
+    int c = 0;
+    L.in0 = c; c += L.in_bytes * kWsStages;
+    L.out0 = c; c += L.out_bytes * 2;
+    L.contrib_bytes = a16((size_t)kNQ * bn * 8);
+    L.contrib = c; c += 2 * L.contrib_bytes;
+    L.sums = c; c += a16((size_t)kNQ * Bt * 8);
+    L.bars = c; c += 8 * (3 * kWsStages + 4);
+    L.total = a16((size_t)c);
+    return L;
+}
+
+template <bool kNorm, bool kAux>
+__global__ void __launch_bounds__(kWsThreads, 3) fleet_step_tma_kernel(const StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.N, D = p.D, Bt = p.Bt;
+    const TmaLayout& L = p.tl;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+    uint64_t* full = bars;                         // [kWsStages] loads of the input stage have landed
+    uint64_t* consumed = bars + kWsStages;         // [kWsStages] every compute thread has read its inputs
+    uint64_t* done = bars + 2 * kWsStages;         // [2]         outputs + contributions of the tile are written
+    uint64_t* ofree = bars + 2 * kWsStages + 2;    // [2]         the bulk stores have read the output buffer and the
+                                                   //             manager has consumed the contribution buffer
+    const int tid = threadIdx.x;
+    const int cstride = Bt * N;
+    const int ntiles = (p.E + Bt - 1) / Bt;
+    const int H = p.Ha + p.Hb;
+
+    if (tid == 0) {
+        for (int s = 0; s < kWsStages; s++) { mbar_init(&full[s], 1); mbar_init(&consumed[s], kWsCompute); }
+        for (int s = 0; s < 2; s++) { mbar_init(&done[s], kWsCompute); mbar_init(&ofree[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int tile0 = blockIdx.x;
+
+    if (tid >= kWsCompute) {
+        // =================================================================== manager warp
+        const int lane = tid - kWsCompute;
+        double* sums = reinterpret_cast<double*>(smem_raw + L.sums);
+        auto load_ev = [&](int tile) -> int4 {
+            const int e = tile * Bt + lane;
+            return (tile < ntiles && lane < Bt && e < p.E) ? p.env4[e] : make_int4(0, 0, 0, 0);
+        };
+        // issue every load of tile `tile` into input stage `s`; ev = env4 of env (tile*Bt + lane) for lane < nb
+        auto issue_tile = [&](int tile, int s, const int4 ev) {
+            const int e0 = tile * Bt;
+            const int nb = min(Bt, p.E - e0);
+            unsigned char* st = smem_raw + L.in0 + (size_t)s * L.in_bytes;
+            const size_t base = (size_t)e0 * N;
+            const uint32_t bn = (uint32_t)(nb * N);
+            if (lane == 0) {
+                const uint32_t bytes = bn * 24u + (uint32_t)nb * (uint32_t)(N * 8 + N * 32 + p.hdr_stride * 4 + 64);
+                mbar_arrive_expect_tx(&full[s], bytes);
+                tma_load(st + L.soc, p.soc + base, bn * 8u, &full[s]);
+                tma_load(st + L.soh, p.soh + base, bn * 8u, &full[s]);
+                tma_load(st + L.act, p.actions + base, bn * 4u, &full[s]);
+                tma_load(st + L.hl, p.hl + base, bn * 4u, &full[s]);
+            }
+            if (lane < nb) {
+                const int e = e0 + lane;
+                const int t = ev.x, k = ev.x - ev.y;
+                const int t1 = min(t + 1, p.T - 1);
+                tma_load(st + L.hist + (size_t)lane * N * 8,
+                         p.hist + (size_t)e * p.RN + (size_t)(p.calc_deg ? k : (k & 1)) * N, (uint32_t)(N * 8), &full[s]);
+                tma_load(st + L.rec + (size_t)lane * N * 32, p.ev_rec + (size_t)t1 * N, (uint32_t)(N * 32), &full[s]);
+                tma_load(st + L.hdr + (size_t)lane * p.hdr_stride * 4, p.hdr + (size_t)t1 * p.hdr_stride,
+                         (uint32_t)(p.hdr_stride * 4), &full[s]);
+                tma_load(st + L.row + (size_t)lane * 64, p.step_row + min(t, p.T - 2), 64u, &full[s]);
+            }
+        };
+        int4 ev_cur[kWsStages];
+#pragma unroll
+        for (int s = 0; s < kWsStages; s++) {
+            const int tl = tile0 + s * gridDim.x;
+            ev_cur[s] = load_ev(tl);
+            if (tl < ntiles) issue_tile(tl, s, ev_cur[s]);
+        }
+        int4 ev_next = load_ev(tile0 + kWsStages * gridDim.x);
+
+        int it = 0;
+        for (int tile = tile0; tile < ntiles; tile += gridDim.x, it++) {
+            const int s = it % kWsStages;
+            const uint32_t parity = (uint32_t)((it / kWsStages) & 1);
+            const int ob = it & 1;
+            const uint32_t oparity = (uint32_t)((it >> 1) & 1);
+            unsigned char* st = smem_raw + L.in0 + (size_t)s * L.in_bytes;
+            unsigned char* so = smem_raw + L.out0 + (size_t)ob * L.out_bytes;
+            const int e0 = tile * Bt;
+            const int nb = min(Bt, p.E - e0);
+            const int nslots = nb * N;
+            int4 ev_mine = make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int q = 0; q < kWsStages; q++) if (q == s) ev_mine = ev_cur[q];
+            const double* contrib = reinterpret_cast<const double*>(smem_raw + L.contrib + ob * L.contrib_bytes);
+
+            // what the manager needs from the input stage, before it is recycled
+            mbar_wait(&full[s], parity);
+            int fl = 0;
+            double gml = 0, pvv = 0;
+            if (lane < nb) {
+                const StepRow* s_row = reinterpret_cast<const StepRow*>(st + L.row);
+                const int t_fin = ev_mine.y + p.L;
+                if (ev_mine.x + 1 == t_fin) fl |= EF_DONE | EF_RESET;
+                if ((s_row[lane].flags_next & TF_TRIGGER) && p.calc_deg) fl |= EF_TRIGGER;
+                gml = s_row[lane].gml; pvv = s_row[lane].pvv;
+            }
+            // ---- refill the input stage with the tile kWsStages ahead as soon as every compute thread has read it
+            const int tile_n = tile + kWsStages * gridDim.x;
+            mbar_wait(&consumed[s], parity);
+            if (tile_n < ntiles) issue_tile(tile_n, s, ev_next);
+#pragma unroll
+            for (int q = 0; q < kWsStages; q++) if (q == s) ev_cur[q] = ev_next;
+            ev_next = load_ev(tile_n + gridDim.x);
+
+            // ---- bulk stores of everything the tile produced
+            mbar_wait(&done[ob], oparity);
+            if (lane == 0) {
+                const size_t base = (size_t)e0 * N;
+                tma_store(p.soc + base, so + L.o_soc, (uint32_t)(nslots * 8));
+                tma_store(p.hl + base, so + L.o_hl, (uint32_t)(nslots * 4));
+            }
+            if (lane < nb) {
+                const int e = e0 + lane;
+                const int k = ev_mine.x - ev_mine.y;
+                tma_store(p.hist + (size_t)e * p.RN + (size_t)(p.calc_deg ? k + 1 : ((k + 1) & 1)) * N,
+                          so + L.o_hist + (size_t)lane * N * 8, (uint32_t)(N * 8));
+                float* dst = (fl & EF_RESET) ? (p.terminal_obs ? p.terminal_obs + (size_t)e * D : nullptr)
+                                             : (p.obs ? p.obs + (size_t)e * D : nullptr);
+                if (dst) tma_store(dst, so + L.o_obs + (size_t)lane * D * 4, (uint32_t)(D * 4));
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+
+            // ---- P2: per-env sums with a FIXED reduction order (deterministic run to run): each lane adds the
+            // env's contributions lane, lane+32, ... in order, then a 5-step shuffle tree combines the 32 partials
+            for (int w = 0; w < kNQ * nb; w++) {
+                const int q = w / nb, bb = w - q * nb;
+                const double* c = contrib + q * cstride + bb * N;
+                double part = 0;
+                for (int nn = lane; nn < N; nn += 32) part += c[nn];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+                if (lane == 0) sums[q * Bt + bb] = part;
+            }
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ofree[ob]);    // output + contribution buffers may be overwritten again
+
+            // ---- P3: one lane per env
+            if (lane < nb) {
+                const int bb = lane, e = e0 + bb;
+                double* stt = p.stats + (size_t)(tile % kStatStripes) * FLEET_S__COUNT;
+                const double cashflow = sums[Q_CASH * Bt + bb];
+                double reward = sums[Q_REWARD * Bt + bb];
+                const double margin = gml - sums[Q_ATH * Bt + bb] * p.evse + pvv;                  // load_calculation.py:93
+                const double overload = fabs(margin < 0.0 ? margin : 0.0);
+                if (overload > 0) {
+                    const double rel = overload / p.grid + 1;                                      // fleet_environment.py:496
+                    const double pen = (rel < 1.1) ? 0.0 : -700 / (1 + exp(-15.77350877 * (rel - 1.33298382)));
+                    reward += pen * p.pen_ovl;                                                     // score_config.py:33-41
+                    atomicAdd(stt + FLEET_S_OVERLOAD_KW, overload);
+                }
+                const double soc_viol = fabs(sums[Q_MISS * Bt + bb]);
+                const double n_viol = sums[Q_NVIOL * Bt + bb];
+                const int dn = (fl & EF_DONE) ? 1 : 0;
+                const double ep_ret = p.env_f64[(size_t)EF_EP_RETURN * p.E + e] + reward;
+                atomicAdd(stt + FLEET_S_STEPS, 1.0);
+                atomicAdd(stt + FLEET_S_REWARD, reward);
+                atomicAdd(stt + FLEET_S_CASHFLOW, cashflow);
+                if (n_viol > 0) { atomicAdd(stt + FLEET_S_SOC_VIOL, soc_viol); atomicAdd(stt + FLEET_S_N_VIOL, n_viol); }
+                if (dn) {
+                    atomicAdd(stt + FLEET_S_EPISODES, 1.0);
+                    atomicAdd(stt + FLEET_S_EP_RETURN, ep_ret);
+                    p.env_f64[(size_t)EF_LAST_EP_RETURN * p.E + e] = ep_ret;
+                }
+                p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
+                p.env4[e] = make_int4(ev_mine.x + 1, ev_mine.y, ev_mine.z, 0);
+                const int wf = ((fl & EF_TRIGGER) ? WL_TRIGGER : 0) | ((fl & EF_RESET) ? WL_RESET : 0);
+                if (wf) {
+                    const int slot = atomicAdd(p.wl_count, 1);
+                    p.wl[slot] = make_int2(e, wf);
+                }
+                p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
+                p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
+                p.env_f64[(size_t)EF_OVERLOAD * p.E + e] = overload;
+                p.env_f64[(size_t)EF_SOC_VIOL * p.E + e] = soc_viol;
+                if (p.reward) p.reward[e] = (float)reward;
+                if (p.done) p.done[e] = (uint8_t)dn;
+            }
+            __syncwarp();
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
+
+    // ======================================================================= compute warps
+    const bool have_flips = (*p.n_flips != 0);
+    int it = 0;
+    for (int tile = tile0; tile < ntiles; tile += gridDim.x, it++) {
+        const int s = it % kWsStages;
+        const uint32_t parity = (uint32_t)((it / kWsStages) & 1);
+        const int ob = it & 1;
+        const unsigned char* st = smem_raw + L.in0 + (size_t)s * L.in_bytes;
+        unsigned char* so = smem_raw + L.out0 + (size_t)ob * L.out_bytes;
+        const int e0 = tile * Bt;
+        const int nb = min(Bt, p.E - e0);
+        const int nslots = nb * N;
+        double* contrib = reinterpret_cast<double*>(smem_raw + L.contrib + ob * L.contrib_bytes);
+        float* obs_tile = reinterpret_cast<float*>(so + L.o_obs);
+
+        mbar_wait(&full[s], parity);
+
+        // ---- read every input of this thread's slot from the stage, then hand the stage back for refilling
+        const int j = tid;
+        const bool active = j < nslots;
+        int b = 0, n = 0;
+        float a32 = 0.f, hl = 0.f;
+        double soc = 0, soh = 1, sdeg = 0;
+        double eS = 0, eFcr = 0, eFdr = 0, eRfac = 0, ePv = 0;
+        uint32_t eflags_next = 0;
+        EvRec rec;
+        rec.sr = 0; rec.tl = 0; rec.there = rec.there_prev = 0; rec.pad = 0; rec.tt = rec.cl = rec.hn = rec.lax = 0;
+        if (active) {
+            b = (int)__umulhi((unsigned)j, p.n_magic);
+            n = j - b * N;
+            const StepRow* es = reinterpret_cast<const StepRow*>(st + L.row) + b;
+            eS = es->S; eFcr = es->F_cr; eFdr = es->F_dr; eRfac = es->Rfac; ePv = es->pv_share; eflags_next = es->flags_next;
+            a32 = reinterpret_cast<const float*>(st + L.act)[j];
+            soc = reinterpret_cast<const double*>(st + L.soc)[j];
+            hl = reinterpret_cast<const float*>(st + L.hl)[j];
+            soh = reinterpret_cast<const double*>(st + L.soh)[j];
+            sdeg = reinterpret_cast<const double*>(st + L.hist)[j];
+            const int4* s_rec = reinterpret_cast<const int4*>(st + L.rec);
+            const int4 v = s_rec[2 * j];
+            const float4 w4 = reinterpret_cast<const float4*>(s_rec)[2 * j + 1];
+            rec.sr = __hiloint2double(v.y, v.x); rec.tl = __int_as_float(v.z);
+            rec.there = (uint8_t)(v.w & 0xff); rec.there_prev = (uint8_t)((v.w >> 8) & 0xff);
+            rec.tt = w4.x; rec.cl = w4.y; rec.hn = w4.z; rec.lax = w4.w;
+        }
+        // time-only part of the observation: first element per thread in a register, the rest (small N) directly
+        float hv = 0.f; int hdst = -1;
+        const float* s_hdr = reinterpret_cast<const float*>(st + L.hdr);
+        if (tid < nb * H) {
+            const int bb = (H == 1) ? tid : (int)__umulhi((unsigned)tid, p.h_magic), q = tid - bb * H;
+            hv = s_hdr[bb * p.hdr_stride + q];
+            hdst = bb * D + (q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha));
+        }
+        if (it >= 2) mbar_wait(&ofree[ob], (uint32_t)(((it >> 1) - 1) & 1));   // output + contribution buffers are free
+        for (int w = kWsCompute + tid; w < nb * H; w += kWsCompute) {
+            const int bb = (H == 1) ? w : (int)__umulhi((unsigned)w, p.h_magic), q = w - bb * H;
+            obs_tile[bb * D + (q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha))] = s_hdr[bb * p.hdr_stride + q];
+        }
+        mbar_arrive(&consumed[s]);
+        if (hdst >= 0) obs_tile[hdst] = hv;
+
+        if (active) {
+            const size_t i = (size_t)e0 * N + j;
+            const bool flip = have_flips && p.tflip[i] != 0;
+            const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
+            const double cap = soh * p.cap0;                                // episode.battery_cap[car]
+            const int there = rec.there_prev;                               // db.There at t
+            const double a = (double)a32;
+            double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
+            double num = 0;
+            if (a >= 0) {                                                   // ev_charger.py:98-156
+                const double dem = (tgt - soc) * cap;
+                const double req = p.P * a * p.dt;
+                if (req * p.eta_c > dem) {
+                    const double d = req - dem;
+                    const double pen = p.pen_oc * (d * d);
+                    c_oc = pen > p.clip_oc ? pen : p.clip_oc;
+                }
+                double en = 0;
+                if (there == 1) en = fmin(dem / p.eta_c, req);              // IEEE divide: SOC must be bit-exact
+                else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
+                num = en * p.eta_c;
+                double ge = en - ePv;
+                ge = ge > 0 ? ge : 0;
+                c_cost = ge * eS * p.mult;
+                c_cr = eFcr * ge;
+            } else if (a < 0) {                                             // ev_charger.py:159-206
+                const double left = -1 * soc * cap;
+                const double req = p.P * a * p.dt;
+                if (req * p.eta_d < left && there != 0) {
+                    const double d = left - req;
+                    c_oc = p.pen_oc * (d * d);
+                }
+                double en = 0.0;
+                if (there == 1) en = fmax(left, req);
+                else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
+                num = en;
+                c_rev = -1 * en * eRfac;
+                c_dr = eFdr * en;
+            } else {
+                atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
+            }
+            const double c_ath = a * (double)there;                         // fleet_environment.py:491
+            if (num != 0) soc = soc + num / cap;                            // ev_charger.py:128,189
+
+            const float ntl = rec.tl;                                       // departure / stay / gone / arrival :528-618
+            if (hl != 0.f && ntl == 0.f) {
+                const double tg = (p.is_ct && (eflags_next & TF_LUNCH)) ? p.target_lunch : tgt;
+                const double diff = tg - soc;
+                if (diff > p.eps) {
+                    c_miss = diff; c_nviol = 1;
+                    c_dep = -500 / (1 + exp(-16.48461585 * (diff - 0.29229767))) + 1;   // score_config.py:26-30
+                } else {
+                    c_dep = p.full_reward;
+                }
+            }
+            if (ntl != 0.f && hl != 0.f) hl -= p.dt_f;
+            else { hl = ntl; soc = rec.sr; }
+            if (soh <= 0.9 && !flip) {                                      // :613-614
+                p.tflip[i] = 1;
+                atomicAdd(p.n_flips, 1);
+            }
+            if (hl != 0.f) sdeg = soc;                                      // :621-623
+
+            reinterpret_cast<double*>(so + L.o_soc)[j] = soc;
+            reinterpret_cast<float*>(so + L.o_hl)[j] = hl;
+            reinterpret_cast<double*>(so + L.o_hist)[j] = sdeg;
+            write_ev_obs<kNorm, kAux>(p, obs_tile + b * D, n, soc, hl, rec, flip);
+            contrib[Q_REWARD * cstride + j] = c_cr + c_dr + c_inv + c_oc + c_dep;
+            contrib[Q_CASH * cstride + j] = -1 * c_cost + c_rev;
+            contrib[Q_ATH * cstride + j] = c_ath;
+            contrib[Q_MISS * cstride + j] = c_miss;
+            contrib[Q_NVIOL * cstride + j] = c_nviol;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (bulk stores)
+        mbar_arrive(&done[ob]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ post kernel
@@ -898,8 +1348,8 @@ struct FleetHandle {
     int64_t bytes = 0;
     int64_t launches = 0;
     std::string err;
-    size_t smem_step = 0, smem_post = 0;
-    int grid = 0, grid_post = 0, need_post = 0, num_sms = 0;
+    size_t smem_step = 0, smem_post = 0, smem_tma = 0;
+    int grid = 0, grid_post = 0, need_post = 0, num_sms = 0, grid_tma = 0, use_tma = 0;
     int max_smem_optin = 0;
     // host-call staging (fleet_step_host)
     float* h_actions_dev = nullptr; float* h_obs_dev = nullptr; float* h_reward_dev = nullptr; uint8_t* h_done_dev = nullptr;
@@ -965,6 +1415,10 @@ StepKernel pick_step(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_step_kernel<true, true> : fleet_step_kernel<true, false>;
     return h->c.aux ? fleet_step_kernel<false, true> : fleet_step_kernel<false, false>;
 }
+StepKernel pick_tma(const FleetHandle* h) {
+    if (h->c.normalize) return h->c.aux ? fleet_step_tma_kernel<true, true> : fleet_step_tma_kernel<true, false>;
+    return h->c.aux ? fleet_step_tma_kernel<false, true> : fleet_step_tma_kernel<false, false>;
+}
 StepKernel pick_post(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_post_kernel<true, true> : fleet_post_kernel<true, false>;
     return h->c.aux ? fleet_post_kernel<false, true> : fleet_post_kernel<false, false>;
@@ -975,6 +1429,10 @@ StepKernel pick_reset(const FleetHandle* h) {
 }
 
 }  // namespace
+
+static void fleet_launch_tma(FleetHandle* h, const StepParams& p, cudaStream_t stream) {
+    pick_tma(h)<<<h->grid_tma, kWsThreads, h->smem_tma, stream>>>(p);
+}
 
 extern "C" {
 
@@ -1029,6 +1487,8 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     cudaDeviceProp prop;
     CUDA_TRY(h, cudaGetDeviceProperties(&prop, device));
     h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    // (a persisting-L2 set-aside for the tables was measured: it shrinks the write-combining capacity for the streaming
+    //  state and made the step 45 % slower, so only per-access evict_last / evict-first hints are used)
 
     // ---- build the HBM tables on the host (float64, reference operation order), then upload
     std::vector<EvRec> rec((size_t)T * N);
@@ -1186,22 +1646,6 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     p.max_hn = (c.target_soc * c.init_battery_cap) / (c.evse_max_power * c.charging_eff);   // :50-51
     p.ev_rec = d_rec; p.step_row = d_rows; p.hdr = d_hdr;
 
-    // exact division by eta_c through its reciprocal (Markstein): verify on the host that the two-FMA correction
-    // reproduces IEEE division for this constant; otherwise the kernel uses a true division.
-    p.eta_c_rcp = 1.0 / c.charging_eff;
-    p.eta_c_rcp_ok = 1;
-    {
-        unsigned long long x = 0x243F6A8885A308D3ull;
-        for (int it = 0; it < 2000000 && p.eta_c_rcp_ok; it++) {
-            x = x * 6364136223846793005ull + 1442695040888963407ull;
-            const double u = (double)(x >> 11) * (1.0 / 9007199254740992.0);      // [0,1)
-            const double a = (it & 1 ? -1.0 : 1.0) * ldexp(u + 0.5, (int)((x >> 3) % 40) - 30);
-            const double q0 = a * p.eta_c_rcp;
-            const double rem = fma(-q0, c.charging_eff, a);
-            const double q = fma(rem, p.eta_c_rcp, q0);
-            if (q != a / c.charging_eff) p.eta_c_rcp_ok = 0;
-        }
-    }
     p.n_magic = (unsigned int)((0x100000000ull + (unsigned long long)N - 1) / (unsigned long long)N);
     {
         const unsigned long long Hh = (unsigned long long)(Ha + Hb > 0 ? Ha + Hb : 1);
@@ -1250,6 +1694,40 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
         if ((rc = dev_alloc(h, &p.post_scratch_i, (size_t)h->grid_post * sc * kPostThreads, false))) return rc;
     }
     h->smem_step = sm;
+    // persistent TMA kernel: applicable when every bulk copy is 16-byte aligned and sized
+    p.Bt = 0;
+    {
+        const char* force = getenv("FLEETSTEP_KERNEL");   // "generic" (default) / "tma"
+        // the persistent TMA kernel is opt-in for now: with ~30 small bulk copies per 200-vehicle tile it is limited by
+        // the per-copy overhead of the copy engine and by the manager warp, and measured no faster than the generic kernel
+        const bool want = (force && strcmp(force, "tma") == 0);
+        if (want && c.auto_reset && (N % 2 == 0) && (h->D % 4 == 0) && N <= kWsCompute && N >= 7) {
+            const int g4 = (N % 4 == 0) ? 1 : 2;               // Bt*N*4 bytes must be a multiple of 16
+            int bt = (kWsCompute / N) / g4 * g4;
+            if (bt > 32) bt = 32 / g4 * g4;                      // one manager lane per env
+            // the last (partial) tile must also give 16-byte sized float32 runs: (E % bt) * N % 4 == 0
+            while (bt >= 1 && (((E % bt) * N) % 4) != 0) bt -= g4;
+            if (bt >= 1) {
+                const TmaLayout L = tma_layout(bt, N, h->D, hdr_stride);
+                int per_sm = 0;
+                if (L.total <= h->max_smem_optin &&
+                    cudaFuncSetAttribute(pick_tma(h), cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) == cudaSuccess &&
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_tma(h), kWsThreads, (size_t)L.total) == cudaSuccess &&
+                    per_sm >= 1) {
+                    p.Bt = bt;
+                    p.tl = L;
+                    h->smem_tma = (size_t)L.total;
+                    const int ntiles = (E + bt - 1) / bt;
+                    const int g = prop.multiProcessorCount * per_sm;
+                    h->grid_tma = g < ntiles ? g : ntiles;
+                    h->use_tma = 1;
+                }
+                cudaGetLastError();
+            }
+        }
+        if (force && strcmp(force, "tma") == 0 && !h->use_tma)
+            return fail(h, FLEET_E_INVALID, "FLEETSTEP_KERNEL=tma requested but the configuration does not qualify (needs auto_reset, even 7 <= N <= 224, D % 4 == 0)");
+    }
     h->grid = (E + p.B - 1) / p.B;
     CUDA_TRY(h, cudaFuncSetAttribute(pick_step(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
 
@@ -1278,7 +1756,8 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     CUDA_TRY(h, cudaSetDevice(h->device));
     StepParams p = h->p;
     p.actions = actions_dev; p.obs = obs_dev; p.reward = reward_dev; p.done = done_dev; p.terminal_obs = terminal_obs_dev;
-    pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
+    if (h->use_tma) fleet_launch_tma(h, p, (cudaStream_t)stream);
+    else pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
     h->launches++;
     if (h->need_post) {   // daily degradation, then auto-reset, for the envs the step kernel put on the work list
         pick_post(h)<<<h->grid_post, kPostThreads, h->smem_post, (cudaStream_t)stream>>>(p);

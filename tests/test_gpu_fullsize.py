@@ -56,13 +56,18 @@ def test_cfg2_full_size_slice_and_invariants():
         # slice vs oracle
         np.testing.assert_array_equal(done[sl].cpu().numpy(), o_done, err_msg=f"done step {s}")
         np.testing.assert_array_equal(obs[sl].cpu().numpy(), o_obs, err_msg=f"obs step {s}")
-        np.testing.assert_array_equal(big.get("soc")[sl].cpu().numpy(), orc.get("soc"), err_msg=f"soc step {s}")
+        # SOC is bit-exact for a given SOH; after a vehicle's first daily degradation its SOH (hence capacity) agrees
+        # with the oracle to 1e-13 only (device pow/exp vs libm), so SOC is compared at the stated tolerance here and
+        # the fraction of elements that are not bit-identical must stay negligible
+        g_soc, o_soc = big.get("soc")[sl].cpu().numpy(), orc.get("soc")
+        np.testing.assert_allclose(g_soc, o_soc, rtol=0, atol=1e-12, err_msg=f"soc step {s}")
+        assert (g_soc != o_soc).mean() < 1e-3
         np.testing.assert_array_equal(big.get("rf_len")[sl].cpu().numpy(), orc.get("rf_len"), err_msg=f"rf_len step {s}")
         np.testing.assert_allclose(big.get("reward64")[sl].cpu().numpy(), o_rew, rtol=1e-11, atol=1e-10)
         np.testing.assert_allclose(big.get("soh")[sl].cpu().numpy(), orc.get("soh"), rtol=0, atol=1e-13)
         # sharding invariance
         assert torch.equal(obs[sl], obs_s), f"shard obs differs at step {s}"
-        assert torch.equal(big.get("soc")[sl], small.get("soc"))
+        assert torch.equal(big.get("soc")[sl], small.get("soc"))      # GPU vs GPU: always bit-identical
         # invariants over all envs
         t_now = big.get("time_idx")
         d = done.bool()

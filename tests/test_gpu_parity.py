@@ -26,12 +26,21 @@ CASES = {
     "lmd_6ev_linear_noaux": dict(n_evs=6, days=12, use_case="lmd", E=40, steps=200, over=dict(deg_mode=1, aux=0)),
     "lmd_5ev_soh09": dict(n_evs=5, days=12, use_case="lmd", E=16, steps=120, over=dict(init_soh=0.9)),
     "lmd_4ev_no_autoreset": dict(n_evs=4, days=12, use_case="lmd", E=8, steps=110, over=dict(auto_reset=0)),
+    # configurations that qualify for the persistent TMA kernel (even N, D % 4 == 0, aligned last tile)
+    "lmd_50ev_e36": dict(n_evs=50, days=8, use_case="lmd", E=36, steps=120),
+    "ut_10ev_e50": dict(n_evs=10, days=10, use_case="ut", E=50, steps=210, episode_hours=48),
 }
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
-def test_gpu_vs_oracle(name):
+# both step-kernel implementations are exercised: "generic" (default) and the opt-in persistent warp-specialised TMA
+# kernel (FLEETSTEP_KERNEL=tma; needs auto-reset, even 7 <= N <= 224, D % 4 == 0)
+KERNELS = [(n, "generic") for n in sorted(CASES)] + [(n, "tma") for n in ("lmd_50ev_e36", "ut_10ev_e50")]
+
+
+@pytest.mark.parametrize("name,kernel", KERNELS)
+def test_gpu_vs_oracle(name, kernel, monkeypatch):
     from fleetrl_b200._lib import FleetStepHandle
+    monkeypatch.setenv("FLEETSTEP_KERNEL", kernel)
 
     cs = dict(CASES[name])
     E, steps = cs.pop("E"), cs.pop("steps")
