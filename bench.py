@@ -94,50 +94,58 @@ def ncu_traffic(args, D):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled through NVML every
+    ~2 ms from a thread (nvidia-smi -lms is too slow to start for a region of tens of milliseconds)."""
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self._stop, self.th, self.err = index, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.err = f"nvml unavailable: {e}"
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception:
+                try:
+                    self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                      nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def mark(self):
+        """samples taken before this point are dropped (call right before the timed region)"""
+        self.rows = []
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.th is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not started"]}
+        self._stop = True
+        self.th.join(timeout=1)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in self.rows))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm),
+                "reasons": reasons, "samples": len(sm)}
 
 
 def cpu_baseline(built, seconds, n_envs, steps_cap=96):
@@ -156,7 +164,7 @@ def cpu_baseline(built, seconds, n_envs, steps_cap=96):
         orc.step_noout(acts[n % 4])
         n += 1
         el = time.perf_counter() - t0
-        if el > seconds or n >= steps_cap * 50:
+        if el > seconds or n >= steps_cap * 1000:
             break
     orc.close()
     return {"value": n_envs * N * n / el, "unit": "EV-steps/s", "cores": cores, "kind": "port",
@@ -250,17 +258,20 @@ def main():
     ptrs = [a.data_ptr() for a in ring]
     o_p, r_p, d_p, t_p = obs.data_ptr(), rew.data_ptr(), done.data_ptr(), term.data_ptr()
 
+    # clocks / throttle reasons are sampled from here on: the warm-up below is the same load as the timed region, which
+    # alone (tens of ms) would be shorter than nvidia-smi's sampling period
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # run one simulated day first so that the timed region sees the steady state (auto-resets, daily evaluations)
     for s in range(W + built.consts.episode_steps):
         h.step_unchecked(ptrs[s % 8], o_p, r_p, d_p, t_p, sp)
     torch.cuda.synchronize(dev)
     h.reset_stats()
 
-    sampler = ClockSampler(local_rank)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    sampler.start()
+    sampler.mark()
     l0 = h.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)

@@ -759,6 +759,335 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
     if (use_bulk && tid == 0) bulk_store_wait_read();   // the tile must stay valid until the bulk copy has read it
 }
 
+// ------------------------------------------------------------------------------ persistent prefetching step kernel
+// Same arithmetic as fleet_step_kernel.  The generic kernel is bound by exposed memory latency: ~57 % of the
+// scheduler cycles have no eligible warp (ncu), because every warp first waits two dependent round trips
+// (env4 -> schedule record / history row) and the 64-register budget caps residency at 32 warps per SM.  Here
+//  * CTAs are persistent (grid = #SMs x resident CTAs) and loop over tiles of B consecutive envs;
+//  * 8 COMPUTE warps: every thread keeps the inputs of the NEXT tile in flight in registers (software pipelining):
+//    the loads of tile i+1 are issued before the arithmetic of tile i, the per-env time index is read two tiles
+//    ahead so that no dependent address ever waits; slot -> (env, EV) mapping and parameter loads are paid once;
+//  * 1 EPILOGUE warp, one tile behind: stages the per-env factors (env4, step_row) of upcoming tiles in shared
+//    memory, sends the finished observation tile to HBM with one TMA bulk store (cp.async.bulk, SASS UBLKCP), does the
+//    per-env sums (one lane per (quantity, env), car order) and the env-level finalisation;
+//  * no CTA-wide barrier in the loop: producer/consumer hand-offs use named barriers (bar.arrive / bar.sync) on
+//    double-buffered contribution + observation tiles and triple-buffered env scratch.
+// Selected when auto_reset is on and 8 <= N <= 256 (one pass per tile); otherwise the generic kernel runs.
+constexpr int kPfCompute = 256;
+constexpr int kPfThreads = kPfCompute + 32;
+
+struct PfEnv {   // per-env scratch of a tile (shared memory, triple buffered)
+    int t, t_start, ep_count, flags;
+    double S, F_cr, F_dr, Rfac, pv_share, gml, pvv;
+};
+
+__host__ __device__ inline size_t pf_smem_bytes(int B, int N, int D) {
+    return align16(3 * align16((size_t)B * sizeof(PfEnv)) + 2 * align16((size_t)kNQ * B * N * 8) + align16((size_t)kNQ * B * 8) +
+                   2 * align16((size_t)B * D * 4));
+}
+
+// named barriers: id 0 is __syncthreads
+__device__ __forceinline__ void nbar_sync(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kPfThreads) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "n"(kPfThreads) : "memory"); }
+constexpr int kBarDone = 1;   // +buf (2): compute -> epilogue: tile written (contributions, obs tile)
+constexpr int kBarFree = 3;   // +buf (2): epilogue -> compute: contribution + obs buffers may be reused
+constexpr int kBarEnv = 5;    // +ebuf (3): epilogue -> compute: env scratch of the tile is staged
+
+template <bool kNorm, bool kAux>
+__global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.N, B = p.B, D = p.D;
+    const int cstride = B * N;
+    const size_t envs_b = align16((size_t)B * sizeof(PfEnv)), contrib_b = align16((size_t)kNQ * cstride * 8);
+    const size_t sums_b = align16((size_t)kNQ * B * 8), obs_b = align16((size_t)B * D * 4);
+    unsigned char* envs0 = smem_raw;
+    unsigned char* contrib0 = smem_raw + 3 * envs_b;
+    double* sums = reinterpret_cast<double*>(contrib0 + 2 * contrib_b);
+    unsigned char* obs0 = reinterpret_cast<unsigned char*>(sums) + sums_b;
+
+    const int tid = threadIdx.x;
+    const int ntiles = (p.E + B - 1) / B;
+    const int H = p.Ha + p.Hb;
+    const uint64_t keep = l2_evict_last_policy();
+    const int tile0 = blockIdx.x, G = gridDim.x;
+
+    if (tid >= kPfCompute) {
+        // =================================================================== epilogue warp
+        const int lane = tid - kPfCompute;
+        int4 envA = make_int4(0, 0, 0, 0), r0, r1, r2, r3;
+        r0 = r1 = r2 = r3 = make_int4(0, 0, 0, 0);
+        auto load_env = [&](int tile) {                       // lane < B: env4 + step_row[t] of env tile*B + lane
+            const int e = tile * B + lane;
+            if (lane < B && tile < ntiles && e < p.E) {
+                envA = ld_keep_v4(p.env4 + e, keep);
+                const int4* r = reinterpret_cast<const int4*>(p.step_row + min(envA.x, p.T - 2));
+                r0 = ld_keep_v4(r, keep); r1 = ld_keep_v4(r + 1, keep); r2 = ld_keep_v4(r + 2, keep); r3 = ld_keep_v4(r + 3, keep);
+            }
+        };
+        auto stage_env = [&](int tile, int ebuf) {
+            const int e = tile * B + lane;
+            if (lane < B && tile < ntiles && e < p.E) {
+                PfEnv& es = reinterpret_cast<PfEnv*>(envs0 + ebuf * envs_b)[lane];
+                es.t = envA.x; es.t_start = envA.y; es.ep_count = envA.z;
+                int fl = 0;
+                if (envA.x + 1 == envA.y + p.L) fl |= EF_DONE | EF_RESET;
+                if (((uint32_t)r3.w & TF_TRIGGER) && p.calc_deg) fl |= EF_TRIGGER;
+                if ((uint32_t)r3.w & TF_LUNCH) fl |= EF_LUNCH;
+                es.flags = fl;
+                es.S = __hiloint2double(r0.y, r0.x); es.F_cr = __hiloint2double(r0.w, r0.z);
+                es.F_dr = __hiloint2double(r1.y, r1.x); es.Rfac = __hiloint2double(r1.w, r1.z);
+                es.pv_share = __hiloint2double(r2.y, r2.x); es.gml = __hiloint2double(r2.w, r2.z);
+                es.pvv = __hiloint2double(r3.y, r3.x);
+            }
+        };
+        // env scratch of the first two tiles
+        load_env(tile0); stage_env(tile0, 0); __syncwarp(); nbar_arrive(kBarEnv + 0);
+        load_env(tile0 + G); stage_env(tile0 + G, 1); __syncwarp(); nbar_arrive(kBarEnv + 1);
+
+        int it = 0;
+        for (int tile = tile0; tile < ntiles; tile += G, it++) {
+            const int buf = it & 1;
+            const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % 3) * envs_b);
+            const double* contrib = reinterpret_cast<const double*>(contrib0 + buf * contrib_b);
+            const float* obs_tile = reinterpret_cast<const float*>(obs0 + buf * obs_b);
+            const int e0 = tile * B;
+            const int nb = min(B, p.E - e0);
+
+            load_env(tile + 2 * G);                           // in flight during this epilogue
+            nbar_sync(kBarDone + buf);                        // the compute warps have written tile `tile`
+
+            // ---- observation tile -> HBM
+            bool any_reset = false;
+            for (int bb = 0; bb < nb; bb++) any_reset |= (envs[bb].flags & EF_RESET) != 0;
+            const bool use_bulk = p.bulk_ok && nb == B && !any_reset && p.obs != nullptr;
+            if (use_bulk) {
+                if (lane == 0) bulk_store_s2g(p.obs + (size_t)e0 * D, obs_tile, (uint32_t)(B * D * 4));
+            } else {
+                for (int w = lane; w < nb * D; w += 32) {
+                    const int bb = w / D;
+                    const int e = e0 + bb;
+                    float* dst = (envs[bb].flags & EF_RESET) ? (p.terminal_obs ? p.terminal_obs + (size_t)e * D : nullptr)
+                                                             : (p.obs ? p.obs + (size_t)e * D : nullptr);
+                    if (dst) dst[w - bb * D] = obs_tile[w];
+                }
+            }
+            // ---- per-env sums: one lane per (quantity, env), sequential in car order (deterministic)
+            for (int w = lane; w < kNQ * nb; w += 32) {
+                const int q = w / nb, bb = w - q * nb;
+                const double* c = contrib + q * cstride + bb * N;
+                double sum = 0;
+#pragma unroll 10
+                for (int nn = 0; nn < N; nn++) sum += c[nn];
+                sums[q * B + bb] = sum;
+            }
+            if (use_bulk && lane == 0) bulk_store_wait_read();
+            __syncwarp();
+            // ---- env scratch of tile +2, then release this tile's buffers
+            stage_env(tile + 2 * G, (it + 2) % 3);
+            __syncwarp();
+            nbar_arrive(kBarEnv + (it + 2) % 3);
+            nbar_arrive(kBarFree + buf);
+
+            // ---- env-level finalisation: one lane per env
+            for (int bb = lane; bb < nb; bb += 32) {
+                const int e = e0 + bb;
+                const PfEnv& es = envs[bb];
+                double* stt = p.stats + (size_t)(tile % kStatStripes) * FLEET_S__COUNT;
+                const double cashflow = sums[Q_CASH * B + bb];
+                double reward = sums[Q_REWARD * B + bb];
+                const double margin = es.gml - sums[Q_ATH * B + bb] * p.evse + es.pvv;             // load_calculation.py:93
+                const double overload = fabs(margin < 0.0 ? margin : 0.0);
+                if (overload > 0) {
+                    const double rel = overload / p.grid + 1;                                      // fleet_environment.py:496
+                    const double pen = (rel < 1.1) ? 0.0 : -700 / (1 + exp(-15.77350877 * (rel - 1.33298382)));
+                    reward += pen * p.pen_ovl;                                                     // score_config.py:33-41
+                    atomicAdd(stt + FLEET_S_OVERLOAD_KW, overload);
+                }
+                const double soc_viol = fabs(sums[Q_MISS * B + bb]);
+                const double n_viol = sums[Q_NVIOL * B + bb];
+                const int dn = (es.flags & EF_DONE) ? 1 : 0;
+                const double ep_ret = p.env_f64[(size_t)EF_EP_RETURN * p.E + e] + reward;
+                atomicAdd(stt + FLEET_S_STEPS, 1.0);
+                atomicAdd(stt + FLEET_S_REWARD, reward);
+                atomicAdd(stt + FLEET_S_CASHFLOW, cashflow);
+                if (n_viol > 0) { atomicAdd(stt + FLEET_S_SOC_VIOL, soc_viol); atomicAdd(stt + FLEET_S_N_VIOL, n_viol); }
+                if (dn) {
+                    atomicAdd(stt + FLEET_S_EPISODES, 1.0);
+                    atomicAdd(stt + FLEET_S_EP_RETURN, ep_ret);
+                    p.env_f64[(size_t)EF_LAST_EP_RETURN * p.E + e] = ep_ret;
+                }
+                p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
+                st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, 0), keep);
+                const int wf = ((es.flags & EF_TRIGGER) ? WL_TRIGGER : 0) | ((es.flags & EF_RESET) ? WL_RESET : 0);
+                if (wf) {
+                    const int sl = atomicAdd(p.wl_count, 1);
+                    p.wl[sl] = make_int2(e, wf);
+                }
+                p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
+                p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
+                p.env_f64[(size_t)EF_OVERLOAD * p.E + e] = overload;
+                p.env_f64[(size_t)EF_SOC_VIOL * p.E + e] = soc_viol;
+                if (p.reward) p.reward[e] = (float)reward;
+                if (p.done) p.done[e] = (uint8_t)dn;
+            }
+            __syncwarp();   // sums[] is reused by the next tile
+        }
+        if (lane == 0) bulk_store_wait_read();
+        return;
+    }
+
+    // ======================================================================= compute warps
+    const bool have_flips = (*p.n_flips != 0);
+    const int j = tid;
+    const int b = (N == 1) ? j : (int)__umulhi((unsigned)j, p.n_magic);     // slot -> (env of tile, EV): same for every tile
+    const int n = j - b * N;
+    const bool slot = j < cstride;
+    const int hpos = n < p.Ha ? 2 * N + n : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (n - p.Ha);
+
+    struct In { float a32, hl, hv; double soc, soh, sdeg; int4 r0, r1; int t, k; };
+    In cur, nxt;
+    cur.a32 = cur.hl = cur.hv = 0.f; cur.soc = cur.sdeg = 0; cur.soh = 1; cur.r0 = cur.r1 = make_int4(0, 0, 0, 0); cur.t = cur.k = 0;
+    nxt = cur;
+    auto load_env4 = [&](int tile) -> int4 {
+        const int e = tile * B + b;
+        return (slot && tile < ntiles && e < p.E) ? ld_keep_v4(p.env4 + e, keep) : make_int4(0, 0, 0, 0);
+    };
+    auto issue_loads = [&](int tile, const int4 ev, In& in) {
+        const int e = tile * B + b;
+        in.t = ev.x; in.k = ev.x - ev.y;
+        if (slot && tile < ntiles && e < p.E) {
+            const size_t i = (size_t)tile * cstride + j;
+            in.a32 = __ldcs(p.actions + i);
+            in.soc = __ldcs(p.soc + i);
+            in.hl = __ldcs(p.hl + i);
+            in.soh = __ldcs(p.soh + i);
+            in.sdeg = __ldcs(p.hist + (size_t)e * p.RN + (unsigned)((p.calc_deg ? in.k : (in.k & 1)) * N + n));
+            const int t1 = min(in.t + 1, p.T - 1);
+            const int4* rp = reinterpret_cast<const int4*>(p.ev_rec + (size_t)t1 * N + n);
+            in.r0 = ld_keep_v4(rp, keep);
+            in.r1 = ld_keep_v4(rp + 1, keep);
+            if (n < H) in.hv = ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + n, keep);
+        }
+    };
+    int4 ev1;
+    {
+        const int4 ev0 = load_env4(tile0);
+        ev1 = load_env4(tile0 + G);
+        issue_loads(tile0, ev0, cur);
+    }
+
+    int it = 0;
+    for (int tile = tile0; tile < ntiles; tile += G, it++) {
+        const int buf = it & 1;
+        const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % 3) * envs_b);
+        double* contrib = reinterpret_cast<double*>(contrib0 + buf * contrib_b);
+        float* obs_tile = reinterpret_cast<float*>(obs0 + buf * obs_b);
+        const int e0 = tile * B;
+        const int nb = min(B, p.E - e0);
+        const bool active = slot && b < nb;
+
+        // ---- loads of the next tile go in flight; env4 two tiles ahead
+        issue_loads(tile + G, ev1, nxt);
+        const int4 ev2 = load_env4(tile + 2 * G);
+
+        nbar_sync(kBarEnv + it % 3);                          // env scratch of this tile is staged
+        if (it >= 2) nbar_sync(kBarFree + buf);               // contribution + obs buffers are free again
+
+        if (active) {
+            const PfEnv& es = envs[b];
+            float* orow = obs_tile + b * D;
+            const size_t i = (size_t)tile * cstride + j;
+            EvRec rec;
+            rec.sr = __hiloint2double(cur.r0.y, cur.r0.x); rec.tl = __int_as_float(cur.r0.z);
+            rec.there = (uint8_t)(cur.r0.w & 0xff); rec.there_prev = (uint8_t)((cur.r0.w >> 8) & 0xff); rec.pad = 0;
+            rec.tt = __int_as_float(cur.r1.x); rec.cl = __int_as_float(cur.r1.y);
+            rec.hn = __int_as_float(cur.r1.z); rec.lax = __int_as_float(cur.r1.w);
+            double soc = cur.soc, sdeg = cur.sdeg;
+            float hl = cur.hl;
+            const double soh = cur.soh;
+            const bool flip = have_flips && p.tflip[i] != 0;
+            const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
+            const double cap = soh * p.cap0;                                // episode.battery_cap[car]
+            const int there = rec.there_prev;                               // db.There at t
+            const double a = (double)cur.a32;
+            double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
+            double num = 0;
+            if (a >= 0) {                                                   // ev_charger.py:98-156
+                const double dem = (tgt - soc) * cap;
+                const double req = p.P * a * p.dt;
+                if (req * p.eta_c > dem) {
+                    const double d = req - dem;
+                    const double pen = p.pen_oc * (d * d);
+                    c_oc = pen > p.clip_oc ? pen : p.clip_oc;
+                }
+                double en = 0;
+                if (there == 1) en = fmin(dem / p.eta_c, req);              // IEEE divide: SOC must be bit-exact
+                else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
+                num = en * p.eta_c;
+                double ge = en - es.pv_share;
+                ge = ge > 0 ? ge : 0;
+                c_cost = ge * es.S * p.mult;
+                c_cr = es.F_cr * ge;
+            } else if (a < 0) {                                             // ev_charger.py:159-206
+                const double left = -1 * soc * cap;
+                const double req = p.P * a * p.dt;
+                if (req * p.eta_d < left && there != 0) {
+                    const double d = left - req;
+                    c_oc = p.pen_oc * (d * d);
+                }
+                double en = 0.0;
+                if (there == 1) en = fmax(left, req);
+                else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
+                num = en;
+                c_rev = -1 * en * es.Rfac;
+                c_dr = es.F_dr * en;
+            } else {
+                atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
+            }
+            const double c_ath = a * (double)there;                         // fleet_environment.py:491
+            if (num != 0) soc = soc + num / cap;                            // ev_charger.py:128,189
+
+            const float ntl = rec.tl;                                       // departure / stay / gone / arrival :528-618
+            if (hl != 0.f && ntl == 0.f) {
+                const double tg = (p.is_ct && (es.flags & EF_LUNCH)) ? p.target_lunch : tgt;
+                const double diff = tg - soc;
+                if (diff > p.eps) {
+                    c_miss = diff; c_nviol = 1;
+                    c_dep = -500 / (1 + exp(-16.48461585 * (diff - 0.29229767))) + 1;   // score_config.py:26-30
+                } else {
+                    c_dep = p.full_reward;
+                }
+            }
+            if (ntl != 0.f && hl != 0.f) hl -= p.dt_f;
+            else { hl = ntl; soc = rec.sr; }
+            if (soh <= 0.9 && !flip) {                                      // :613-614
+                p.tflip[i] = 1;
+                atomicAdd(p.n_flips, 1);
+            }
+            if (hl != 0.f) sdeg = soc;                                      // :621-623
+
+            __stcs(p.soc + i, soc);
+            __stcs(p.hl + i, hl);
+            __stcs(p.hist + (size_t)(e0 + b) * p.RN + (unsigned)((p.calc_deg ? cur.k + 1 : ((cur.k + 1) & 1)) * N + n), sdeg);
+            write_ev_obs<kNorm, kAux>(p, orow, n, soc, hl, rec, flip);
+            // time-only part of the observation: element n of this env's header row (+ the rest when N < H)
+            if (n < H) orow[hpos] = cur.hv;
+            for (int q = n + N; q < H; q += N)
+                orow[q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha)] =
+                    ld_keep_f32(p.hdr + (size_t)min(cur.t + 1, p.T - 1) * p.hdr_stride + q, keep);
+            contrib[Q_REWARD * cstride + j] = c_cr + c_dr + c_inv + c_oc + c_dep;
+            contrib[Q_CASH * cstride + j] = -1 * c_cost + c_rev;
+            contrib[Q_ATH * cstride + j] = c_ath;
+            contrib[Q_MISS * cstride + j] = c_miss;
+            contrib[Q_NVIOL * cstride + j] = c_nviol;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (bulk store)
+        nbar_arrive(kBarDone + buf);
+        cur = nxt;
+        ev1 = ev2;
+    }
+}
+
 // ------------------------------------------------------------------------------------- persistent TMA step kernel
 // Same arithmetic as fleet_step_kernel, restructured for latency hiding and fewer per-thread instructions:
 //  * persistent CTAs (grid = #SMs x resident CTAs) loop over tiles of Bt consecutive envs;
@@ -1348,7 +1677,8 @@ struct FleetHandle {
     int64_t bytes = 0;
     int64_t launches = 0;
     std::string err;
-    size_t smem_step = 0, smem_post = 0, smem_tma = 0;
+    size_t smem_step = 0, smem_post = 0, smem_tma = 0, smem_pf = 0;
+    int grid_pf = 0, use_pf = 0;
     int grid = 0, grid_post = 0, need_post = 0, num_sms = 0, grid_tma = 0, use_tma = 0;
     int max_smem_optin = 0;
     // host-call staging (fleet_step_host)
@@ -1414,6 +1744,10 @@ using StepKernel = void (*)(const StepParams);
 StepKernel pick_step(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_step_kernel<true, true> : fleet_step_kernel<true, false>;
     return h->c.aux ? fleet_step_kernel<false, true> : fleet_step_kernel<false, false>;
+}
+StepKernel pick_pf(const FleetHandle* h) {
+    if (h->c.normalize) return h->c.aux ? fleet_step_pf_kernel<true, true> : fleet_step_pf_kernel<true, false>;
+    return h->c.aux ? fleet_step_pf_kernel<false, true> : fleet_step_pf_kernel<false, false>;
 }
 StepKernel pick_tma(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_step_tma_kernel<true, true> : fleet_step_tma_kernel<true, false>;
@@ -1694,6 +2028,27 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
         if ((rc = dev_alloc(h, &p.post_scratch_i, (size_t)h->grid_post * sc * kPostThreads, false))) return rc;
     }
     h->smem_step = sm;
+    // persistent prefetching kernel (default where applicable)
+    {
+        const char* force = getenv("FLEETSTEP_KERNEL");   // "generic" / "pf" / "tma"; default: pf when applicable
+        const bool want = !force || strcmp(force, "pf") == 0;
+        if (want && c.auto_reset && N >= 8 && p.B * N <= kPfThreads) {
+            const size_t smpf = pf_smem_bytes(p.B, N, h->D);
+            int per_sm = 0;
+            if ((int64_t)smpf <= (int64_t)h->max_smem_optin &&
+                cudaFuncSetAttribute(pick_pf(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smpf) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_pf(h), kPfThreads, smpf) == cudaSuccess && per_sm >= 1) {
+                h->smem_pf = smpf;
+                const int ntiles = (E + p.B - 1) / p.B;
+                const int g = prop.multiProcessorCount * per_sm;
+                h->grid_pf = g < ntiles ? g : ntiles;
+                h->use_pf = 1;
+            }
+            cudaGetLastError();
+        }
+        if (force && strcmp(force, "pf") == 0 && !h->use_pf)
+            return fail(h, FLEET_E_INVALID, "FLEETSTEP_KERNEL=pf requested but the configuration does not qualify (needs auto_reset, 8 <= N <= 256)");
+    }
     // persistent TMA kernel: applicable when every bulk copy is 16-byte aligned and sized
     p.Bt = 0;
     {
@@ -1757,6 +2112,7 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     StepParams p = h->p;
     p.actions = actions_dev; p.obs = obs_dev; p.reward = reward_dev; p.done = done_dev; p.terminal_obs = terminal_obs_dev;
     if (h->use_tma) fleet_launch_tma(h, p, (cudaStream_t)stream);
+    else if (h->use_pf) pick_pf(h)<<<h->grid_pf, kPfThreads, h->smem_pf, (cudaStream_t)stream>>>(p);
     else pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
     h->launches++;
     if (h->need_post) {   // daily degradation, then auto-reset, for the envs the step kernel put on the work list
