@@ -309,7 +309,7 @@ __device__ __forceinline__ void reset_slot(const StepParams& p, int e, int n, in
 //   evaluated with all lanes of the warp active.
 // max(End) of the list is always len-1 (the provisional last reversal closes the last half cycle), :138.
 constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one work-list env per CTA)
-constexpr int kStackS = 32;   // shared-memory ring depth; deeper stacks fall back to a global-memory scratch ring
+constexpr int kStackS = 16;   // shared-memory ring depth; deeper stacks fall back to a global-memory scratch ring
 
 struct RfRing {               // stack storage: entry k lives at [(k & mask) * stride]
     double* v;
@@ -319,81 +319,100 @@ struct RfRing {               // stack storage: entry k lives at [(k & mask) * s
 
 struct RfOut { int m; double mean_sum; bool overflow; };
 
-constexpr int kRfBatch = 16;  // history samples prefetched per batch (independent loads in flight per thread)
+constexpr int kRfBatch = 16;  // history samples / reversal values prefetched per batch (independent loads in flight)
 
+// Two phases, both streaming the history with batched prefetch:
+//  A. reversal detection (rainflow.reversals): branch-free per sample; the sample indices of the reversal points are
+//     compacted into `ridx` (shared memory, one 16-bit entry per point).  First and last samples are reversals;
+//     plateaus are skipped with an exact ==; the index reported for a plateau is its last sample.
+//  B. the three-point stack (rainflow.extract_cycles) over the compacted reversal list only, values fetched by
+//     index in batches.
 // kShared: ring in shared memory with compile-time geometry (mask kStackS-1, stride kPostThreads).
-// xs: per-thread staging of one prefetched batch, xs[u * kPostThreads] (shared memory).
 template <bool kShared>
 __device__ __forceinline__ RfOut rainflow_pass1(const double* __restrict__ x, int xstride, int len, RfRing rg,
-                                                uint32_t* __restrict__ recs, double* __restrict__ xs) {
+                                                uint32_t* __restrict__ recs, uint16_t* __restrict__ ridx) {
     RfOut out; out.m = 0; out.mean_sum = 0; out.overflow = false;
     if (len < 2) return out;
+    const int mask = kShared ? (kStackS - 1) : rg.mask;
+    const int stride = kShared ? kPostThreads : rg.stride;
+    const int cap_ring = mask + 1;
+
+    // ---- phase A
+    int nr = 0;                                   // reversal points found so far
+    ridx[0] = 0; nr = 1;                          // yield (0, x0)
+    {
+        const double x0 = __ldcs(x), x1 = __ldcs(x + xstride);
+        double xc = x1, d_last = x1 - x0;
+        for (int pos0 = 2; pos0 < len; pos0 += kRfBatch) {
+            double xb[kRfBatch];
+#pragma unroll
+            for (int u = 0; u < kRfBatch; u++)   // clamped index, no select: all loads of the batch issue back to back
+                xb[u] = __ldcs(x + (size_t)min(pos0 + u, len - 1) * xstride);
+#pragma unroll
+            for (int u = 0; u < kRfBatch; u++) {
+                const int pos = pos0 + u;
+                const double x_next = xb[u];
+                const bool ne = (pos < len) && (x_next != xc);
+                const double d_next = x_next - xc;
+                const bool rev = ne && (d_last * d_next < 0);
+                if (rev) { ridx[nr * kPostThreads] = (uint16_t)(pos - 1); nr++; }
+                if (ne) { xc = x_next; d_last = d_next; }
+            }
+        }
+        if (len >= 3) { ridx[nr * kPostThreads] = (uint16_t)(len - 1); nr++; }   // the last sample closes the series
+    }
+
+    // ---- phase B
     int lo = 0, hi = 0, m = 0;
     double mean_sum = 0;
     double v1 = 0, v2 = 0, v3 = 0;     // values of the top three stack entries (v3 = top)
     int i1 = 0, i2 = 0, i3 = 0;        // their sample indices
     bool overflow = false;
-    const int mask = kShared ? (kStackS - 1) : rg.mask;
-    const int stride = kShared ? kPostThreads : rg.stride;
-    const int cap_ring = mask + 1;
-
 #define RF_SLOT(k) (((k) & mask) * stride)
-#define RF_EMIT(ia, xa, ib, xb, full)                                                            \
+#define RF_EMIT(ia, xa, ib, xb_, full)                                                           \
     do {                                                                                         \
-        mean_sum += 0.5 * ((xa) + (xb));                                                         \
+        mean_sum += 0.5 * ((xa) + (xb_));                                                        \
         recs[m * kPostThreads] = (uint32_t)(ia) | ((uint32_t)(ib) << 15) | ((uint32_t)(full) << 30);  \
         m++;                                                                                     \
     } while (0)
-#define RF_PUSH(idx, val)                                                                        \
-    do {                                                                                         \
-        if (hi - lo >= cap_ring) { overflow = true; break; }                                     \
-        rg.v[RF_SLOT(hi)] = (val); rg.i[RF_SLOT(hi)] = (uint16_t)(idx); hi++;                    \
-        v1 = v2; i1 = i2; v2 = v3; i2 = i3; v3 = (val); i3 = (idx);                              \
-        while (hi - lo >= 3) {                                                                   \
-            const double X = fabs(v3 - v2), Y = fabs(v2 - v1);                                   \
-            if (X < Y) break;                                                                    \
-            if (hi - lo == 3) { RF_EMIT(i1, v1, i2, v2, 0); lo++; }                              \
-            else {                                                                               \
-                RF_EMIT(i1, v1, i2, v2, 1);                                                      \
-                hi -= 2;                                                                         \
-                rg.v[RF_SLOT(hi - 1)] = v3; rg.i[RF_SLOT(hi - 1)] = (uint16_t)i3;                \
-                v2 = rg.v[RF_SLOT(hi - 2)]; i2 = rg.i[RF_SLOT(hi - 2)];                          \
-                if (hi - lo >= 3) { v1 = rg.v[RF_SLOT(hi - 3)]; i1 = rg.i[RF_SLOT(hi - 3)]; }    \
-            }                                                                                    \
-        }                                                                                        \
-    } while (0)
-
-    const double x0 = __ldcs(x), x1 = __ldcs(x + xstride);
-    double xc = x1, d_last = x1 - x0;
-    RF_PUSH(0, x0);
-    int index = -1;
-    double x_next = 0;
-    for (int pos0 = 2; pos0 < len && !overflow; pos0 += kRfBatch) {
-        double xb[kRfBatch];
+    for (int r0 = 0; r0 < nr && !overflow; r0 += kRfBatch) {
+        double vb[kRfBatch];
+        int ib_[kRfBatch];
 #pragma unroll
-        for (int u = 0; u < kRfBatch; u++)
-            xb[u] = (pos0 + u < len) ? __ldcs(x + (size_t)(pos0 + u) * xstride) : 0.0;
+        for (int u = 0; u < kRfBatch; u++) ib_[u] = (int)ridx[min(r0 + u, nr - 1) * kPostThreads];
 #pragma unroll
-        for (int u = 0; u < kRfBatch; u++) xs[u * kPostThreads] = xb[u];
-        const int nbatch = min(kRfBatch, len - pos0);
-        for (int u = 0; u < nbatch && !overflow; u++) {
-            index = pos0 + u - 1;
-            x_next = xs[u * kPostThreads];
-            if (x_next != xc) {
-                const double d_next = x_next - xc;
-                if (d_last * d_next < 0) RF_PUSH(index, xc);
-                xc = x_next; d_last = d_next;
+        for (int u = 0; u < kRfBatch; u++) vb[u] = x[(size_t)ib_[u] * xstride];
+#pragma unroll
+        for (int u = 0; u < kRfBatch; u++) {
+            if (r0 + u < nr && !overflow) {
+                const double val = vb[u];
+                const int idx = ib_[u];
+                if (hi - lo >= cap_ring) { overflow = true; }
+                else {
+                    rg.v[RF_SLOT(hi)] = val; rg.i[RF_SLOT(hi)] = (uint16_t)idx; hi++;
+                    v1 = v2; i1 = i2; v2 = v3; i2 = i3; v3 = val; i3 = idx;
+                    while (hi - lo >= 3) {
+                        const double X = fabs(v3 - v2), Y = fabs(v2 - v1);
+                        if (X < Y) break;
+                        if (hi - lo == 3) { RF_EMIT(i1, v1, i2, v2, 0); lo++; }
+                        else {
+                            RF_EMIT(i1, v1, i2, v2, 1);
+                            hi -= 2;
+                            rg.v[RF_SLOT(hi - 1)] = v3; rg.i[RF_SLOT(hi - 1)] = (uint16_t)i3;
+                            v2 = rg.v[RF_SLOT(hi - 2)]; i2 = rg.i[RF_SLOT(hi - 2)];
+                            if (hi - lo >= 3) { v1 = rg.v[RF_SLOT(hi - 3)]; i1 = rg.i[RF_SLOT(hi - 3)]; }
+                        }
+                    }
+                }
             }
         }
     }
-    if (index >= 0 && !overflow) RF_PUSH(index + 1, x_next);
     while (hi - lo > 1 && !overflow) {
         const double xa = rg.v[RF_SLOT(lo)], xb2 = rg.v[RF_SLOT(lo + 1)];
-        const int ia = rg.i[RF_SLOT(lo)], ib = rg.i[RF_SLOT(lo + 1)];
-        RF_EMIT(ia, xa, ib, xb2, 0);
+        const int ia = rg.i[RF_SLOT(lo)], ib2 = rg.i[RF_SLOT(lo + 1)];
+        RF_EMIT(ia, xa, ib2, xb2, 0);
         lo++;
     }
-#undef RF_PUSH
 #undef RF_EMIT
 #undef RF_SLOT
     out.m = m; out.mean_sum = mean_sum; out.overflow = overflow;
@@ -854,6 +873,8 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
             const int nb = min(B, p.E - e0);
 
             load_env(tile + 2 * G);                           // in flight during this epilogue
+            double ep_prev = 0;                               // episode return so far (lane < nb), fetched ahead of its use
+            if (lane < nb) ep_prev = p.env_f64[(size_t)EF_EP_RETURN * p.E + e0 + lane];
             nbar_sync(kBarDone + buf);                        // the compute warps have written tile `tile`
 
             // ---- observation tile -> HBM
@@ -882,11 +903,10 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
             }
             if (use_bulk && lane == 0) bulk_store_wait_read();
             __syncwarp();
-            // ---- env scratch of tile +2, then release this tile's buffers
             stage_env(tile + 2 * G, (it + 2) % 3);
             __syncwarp();
             nbar_arrive(kBarEnv + (it + 2) % 3);
-            nbar_arrive(kBarFree + buf);
+            nbar_arrive(kBarFree + buf);                      // contribution + obs buffers of this tile are free again
 
             // ---- env-level finalisation: one lane per env
             for (int bb = lane; bb < nb; bb += 32) {
@@ -906,7 +926,7 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
                 const double soc_viol = fabs(sums[Q_MISS * B + bb]);
                 const double n_viol = sums[Q_NVIOL * B + bb];
                 const int dn = (es.flags & EF_DONE) ? 1 : 0;
-                const double ep_ret = p.env_f64[(size_t)EF_EP_RETURN * p.E + e] + reward;
+                const double ep_ret = ((bb == lane) ? ep_prev : p.env_f64[(size_t)EF_EP_RETURN * p.E + e]) + reward;
                 atomicAdd(stt + FLEET_S_STEPS, 1.0);
                 atomicAdd(stt + FLEET_S_REWARD, reward);
                 atomicAdd(stt + FLEET_S_CASHFLOW, cashflow);
@@ -944,17 +964,24 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
     const bool slot = j < cstride;
     const int hpos = n < p.Ha ? 2 * N + n : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (n - p.Ha);
 
-    struct In { float a32, hl, hv; double soc, soh, sdeg; int4 r0, r1; int t, k; };
+    // pipeline registers: only what the arithmetic needs up front is prefetched one tile ahead; the second half of the
+    // schedule record (auxiliary observation terms) and the header element are loaded at the start of the tile and
+    // consumed at its end, which keeps the register footprint below the 3-CTA budget without spills
+    struct In { float a32, hl; double soc, soh, sdeg; int4 r0; int k; };
     In cur, nxt;
-    cur.a32 = cur.hl = cur.hv = 0.f; cur.soc = cur.sdeg = 0; cur.soh = 1; cur.r0 = cur.r1 = make_int4(0, 0, 0, 0); cur.t = cur.k = 0;
+    cur.a32 = cur.hl = 0.f; cur.soc = cur.sdeg = 0; cur.soh = 1; cur.r0 = make_int4(0, 0, 0, 0); cur.k = 0;
     nxt = cur;
-    auto load_env4 = [&](int tile) -> int4 {
+    auto load_env2 = [&](int tile) -> int2 {
         const int e = tile * B + b;
-        return (slot && tile < ntiles && e < p.E) ? ld_keep_v4(p.env4 + e, keep) : make_int4(0, 0, 0, 0);
+        int2 v = make_int2(0, 0);
+        if (slot && tile < ntiles && e < p.E) {   // predicated load straight into the pipeline register (a select here
+            asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "+r"(v.x), "+r"(v.y) : "l"(p.env4 + e));   // would wait on it)
+        }
+        return v;
     };
-    auto issue_loads = [&](int tile, const int4 ev, In& in) {
+    auto issue_loads = [&](int tile, const int2 ev, In& in) {
         const int e = tile * B + b;
-        in.t = ev.x; in.k = ev.x - ev.y;
+        in.k = ev.x - ev.y;
         if (slot && tile < ntiles && e < p.E) {
             const size_t i = (size_t)tile * cstride + j;
             in.a32 = __ldcs(p.actions + i);
@@ -962,17 +989,13 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
             in.hl = __ldcs(p.hl + i);
             in.soh = __ldcs(p.soh + i);
             in.sdeg = __ldcs(p.hist + (size_t)e * p.RN + (unsigned)((p.calc_deg ? in.k : (in.k & 1)) * N + n));
-            const int t1 = min(in.t + 1, p.T - 1);
-            const int4* rp = reinterpret_cast<const int4*>(p.ev_rec + (size_t)t1 * N + n);
-            in.r0 = ld_keep_v4(rp, keep);
-            in.r1 = ld_keep_v4(rp + 1, keep);
-            if (n < H) in.hv = ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + n, keep);
+            in.r0 = ld_keep_v4(p.ev_rec + (size_t)min(ev.x + 1, p.T - 1) * N + n, keep);
         }
     };
-    int4 ev1;
+    int2 ev1;
     {
-        const int4 ev0 = load_env4(tile0);
-        ev1 = load_env4(tile0 + G);
+        const int2 ev0 = load_env2(tile0);
+        ev1 = load_env2(tile0 + G);
         issue_loads(tile0, ev0, cur);
     }
 
@@ -988,7 +1011,7 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
 
         // ---- loads of the next tile go in flight; env4 two tiles ahead
         issue_loads(tile + G, ev1, nxt);
-        const int4 ev2 = load_env4(tile + 2 * G);
+        const int2 ev2 = load_env2(tile + 2 * G);
 
         nbar_sync(kBarEnv + it % 3);                          // env scratch of this tile is staged
         if (it >= 2) nbar_sync(kBarFree + buf);               // contribution + obs buffers are free again
@@ -997,11 +1020,14 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
             const PfEnv& es = envs[b];
             float* orow = obs_tile + b * D;
             const size_t i = (size_t)tile * cstride + j;
+            // issued now, consumed by the observation stores at the end of the tile
+            const int t1 = min(es.t + 1, p.T - 1);
+            const int4 r1 = ld_keep_v4(reinterpret_cast<const int4*>(p.ev_rec + (size_t)t1 * N + n) + 1, keep);
+            float hv = 0.f;
+            if (n < H) hv = ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + n, keep);
             EvRec rec;
             rec.sr = __hiloint2double(cur.r0.y, cur.r0.x); rec.tl = __int_as_float(cur.r0.z);
             rec.there = (uint8_t)(cur.r0.w & 0xff); rec.there_prev = (uint8_t)((cur.r0.w >> 8) & 0xff); rec.pad = 0;
-            rec.tt = __int_as_float(cur.r1.x); rec.cl = __int_as_float(cur.r1.y);
-            rec.hn = __int_as_float(cur.r1.z); rec.lax = __int_as_float(cur.r1.w);
             double soc = cur.soc, sdeg = cur.sdeg;
             float hl = cur.hl;
             const double soh = cur.soh;
@@ -1069,17 +1095,19 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
             __stcs(p.soc + i, soc);
             __stcs(p.hl + i, hl);
             __stcs(p.hist + (size_t)(e0 + b) * p.RN + (unsigned)((p.calc_deg ? cur.k + 1 : ((cur.k + 1) & 1)) * N + n), sdeg);
-            write_ev_obs<kNorm, kAux>(p, orow, n, soc, hl, rec, flip);
-            // time-only part of the observation: element n of this env's header row (+ the rest when N < H)
-            if (n < H) orow[hpos] = cur.hv;
-            for (int q = n + N; q < H; q += N)
-                orow[q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha)] =
-                    ld_keep_f32(p.hdr + (size_t)min(cur.t + 1, p.T - 1) * p.hdr_stride + q, keep);
             contrib[Q_REWARD * cstride + j] = c_cr + c_dr + c_inv + c_oc + c_dep;
             contrib[Q_CASH * cstride + j] = -1 * c_cost + c_rev;
             contrib[Q_ATH * cstride + j] = c_ath;
             contrib[Q_MISS * cstride + j] = c_miss;
             contrib[Q_NVIOL * cstride + j] = c_nviol;
+            rec.tt = __int_as_float(r1.x); rec.cl = __int_as_float(r1.y);
+            rec.hn = __int_as_float(r1.z); rec.lax = __int_as_float(r1.w);
+            write_ev_obs<kNorm, kAux>(p, orow, n, soc, hl, rec, flip);
+            // time-only part of the observation: element n of this env's header row (+ the rest when N < H)
+            if (n < H) orow[hpos] = hv;
+            for (int q = n + N; q < H; q += N)
+                orow[q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha)] =
+                    ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + q, keep);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (bulk store)
         nbar_arrive(kBarDone + buf);
@@ -1506,9 +1534,9 @@ __global__ void __launch_bounds__(kWsThreads, 3) fleet_step_tma_kernel(const Ste
 // doubles) is first staged into shared memory with coalesced, deeply unrolled loads; each thread then streams its
 // vehicle's column through the three-point rainflow with an index stack in shared memory.
 __host__ __device__ inline size_t post_smem_bytes(int cap) {
-    // value ring [kStackS][64] f64 | batch staging [kRfBatch][64] f64 | index ring [kStackS][64] u16 | records [cap][64] u32
-    return align16((size_t)kStackS * kPostThreads * 8 + (size_t)kRfBatch * kPostThreads * 8 + (size_t)kStackS * kPostThreads * 2 +
-                   (size_t)cap * kPostThreads * 4);
+    // value ring [kStackS][64] f64 | records [cap][64] u32 | index ring [kStackS][64] u16 | reversal indices [cap][64] u16
+    return align16((size_t)kStackS * kPostThreads * 8 + (size_t)cap * kPostThreads * 4 + (size_t)kStackS * kPostThreads * 2 +
+                   (size_t)cap * kPostThreads * 2);
 }
 
 template <bool kNorm, bool kAux>
@@ -1516,9 +1544,10 @@ __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepPara
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N, D = p.D;
     double* vring = reinterpret_cast<double*>(smem_raw);
-    double* xstage = vring + kStackS * kPostThreads;
-    uint16_t* iring = reinterpret_cast<uint16_t*>(xstage + kRfBatch * kPostThreads);
-    uint32_t* recs = reinterpret_cast<uint32_t*>(iring + kStackS * kPostThreads);
+    const int cap = p.L + 2;
+    uint32_t* recs = reinterpret_cast<uint32_t*>(vring + kStackS * kPostThreads);
+    uint16_t* iring = reinterpret_cast<uint16_t*>(recs + cap * kPostThreads);
+    uint16_t* ridx = iring + kStackS * kPostThreads;
     __shared__ double s_deg;
     const int tid = threadIdx.x;
     const int count = *p.wl_count;
@@ -1542,13 +1571,13 @@ __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepPara
                         p.n_cycles[ii] = 0;
                     } else {
                         RfRing rg; rg.v = vring + tid; rg.i = iring + tid; rg.mask = kStackS - 1; rg.stride = kPostThreads;
-                        RfOut r = rainflow_pass1<true>(hcol, N, len, rg, recs + tid, xstage + tid);
+                        RfOut r = rainflow_pass1<true>(hcol, N, len, rg, recs + tid, ridx + tid);
                         if (r.overflow) {   // stack deeper than the shared ring: redo with the global scratch ring
                             RfRing gg;
                             gg.v = p.post_scratch_v + ((size_t)blockIdx.x * p.scratch_cap) * kPostThreads + tid;
                             gg.i = p.post_scratch_i + ((size_t)blockIdx.x * p.scratch_cap) * kPostThreads + tid;
                             gg.mask = p.scratch_cap - 1; gg.stride = kPostThreads;
-                            r = rainflow_pass1<false>(hcol, N, len, gg, recs + tid, xstage + tid);
+                            r = rainflow_pass1<false>(hcol, N, len, gg, recs + tid, ridx + tid);
                         }
                         deg = sei_finish(p, ii, hcol, N, len, r, recs + tid);
                     }
