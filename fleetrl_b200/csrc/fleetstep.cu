@@ -124,9 +124,12 @@ struct StepParams {
     double* stats;            // [kStatStripes][FLEET_S__COUNT]
     unsigned int* err_flags;  // [1]
     const int* next_start;    // [E] or nullptr
-    int2* wl;                 // [E] work list of the post kernel: {env, WL_* flags}
-    int* wl_count;            // [1]
+    int2* wl;                 // [E] work list of the post kernel, degradation entries: {env, WL_* flags}
+    int* wlr;                 // [E] work list of the post kernel, reset-only entries: env
+    int* wl_count;            // [4] {degradation entries, reset-only entries, next degradation entry, next reset entry}
     unsigned int* wl_done;    // [1]
+    int po_nc, po_lp, po_g;   // cooperative post kernel: vehicles per chunk, column pitch (odd), threads per vehicle in pass 2
+    int po_stk, po_recs, po_misc;   // its shared-memory offsets (bytes)
     double* post_scratch_v;   // [grid_post][scratch_cap][64] fallback rainflow value ring
     uint16_t* post_scratch_i; // [grid_post][scratch_cap][64]
     int scratch_cap;          // power of two >= L+2
@@ -308,6 +311,14 @@ __device__ __forceinline__ void reset_slot(const StepParams& p, int e, int n, in
 //   (:146); the recorded cycles a <= j < m-1 are replayed in list order and the SEI stress terms (pow/exp) are
 //   evaluated with all lanes of the warp active.
 // max(End) of the list is always len-1 (the provisional last reversal closes the last half cycle), :138.
+#ifdef POST_TIMING
+__device__ unsigned long long g_post_clk[16];
+#define PT_MARK(k) do { if ((threadIdx.x & 31) == 0) { const long long _c = clock64(); atomicAdd(&g_post_clk[k], (unsigned long long)(_c - _pt)); _pt = _c; } } while (0)
+#define PT_START() long long _pt = clock64()
+#else
+#define PT_MARK(k) do {} while (0)
+#define PT_START() do {} while (0)
+#endif
 constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one work-list env per CTA)
 constexpr int kStackS = 16;   // shared-memory ring depth; deeper stacks fall back to a global-memory scratch ring
 
@@ -336,6 +347,7 @@ __device__ __forceinline__ RfOut rainflow_pass1(const double* __restrict__ x, in
     const int mask = kShared ? (kStackS - 1) : rg.mask;
     const int stride = kShared ? kPostThreads : rg.stride;
     const int cap_ring = mask + 1;
+    PT_START();
 
     // ---- phase A
     int nr = 0;                                   // reversal points found so far
@@ -362,6 +374,7 @@ __device__ __forceinline__ RfOut rainflow_pass1(const double* __restrict__ x, in
         if (len >= 3) { ridx[nr * kPostThreads] = (uint16_t)(len - 1); nr++; }   // the last sample closes the series
     }
 
+    PT_MARK(0);
     // ---- phase B
     int lo = 0, hi = 0, m = 0;
     double mean_sum = 0;
@@ -407,6 +420,7 @@ __device__ __forceinline__ RfOut rainflow_pass1(const double* __restrict__ x, in
             }
         }
     }
+    PT_MARK(1);
     while (hi - lo > 1 && !overflow) {
         const double xa = rg.v[RF_SLOT(lo)], xb2 = rg.v[RF_SLOT(lo + 1)];
         const int ia = rg.i[RF_SLOT(lo)], ib2 = rg.i[RF_SLOT(lo + 1)];
@@ -415,6 +429,10 @@ __device__ __forceinline__ RfOut rainflow_pass1(const double* __restrict__ x, in
     }
 #undef RF_EMIT
 #undef RF_SLOT
+    PT_MARK(2);
+#ifdef POST_TIMING
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&g_post_clk[8], (unsigned long long)nr); atomicAdd(&g_post_clk[9], (unsigned long long)m); atomicAdd(&g_post_clk[10], 1ull); }
+#endif
     out.m = m; out.mean_sum = mean_sum; out.overflow = overflow;
     return out;
 }
@@ -424,10 +442,14 @@ __device__ __forceinline__ double sei_finish(const StepParams& p, size_t i, cons
                                              int len, const RfOut r, const uint32_t* __restrict__ recs) {
     const double alpha_sei = 5.75E-2, beta_sei = 121, k_sigma = 1.04, sigma_ref = 0.5, k_temp = 6.93E-2,
                  temp_ref = 25, k_dt = 4.14E-10, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
+    PT_START();
     const int rf_len = p.rf_len[i];
     const int m = r.m;
     p.n_cycles[i] = m;
     double deg = 0;
+#ifdef POST_TIMING
+    if ((threadIdx.x & 31) == 0 && m > rf_len) atomicAdd(&g_post_clk[11], (unsigned long long)(m - rf_len));
+#endif
     if (m > rf_len) {                                                                  // :143
         const double s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
         double fsum = 0, max_dod = 0;
@@ -442,6 +464,7 @@ __device__ __forceinline__ double sei_finish(const StepParams& p, size_t i, cons
             fsum += s_dod * s_soc * s_temp;                                            // :77-79, np.sum :174
             if (range > max_dod) max_dod = range;
         }
+        PT_MARK(3);
         const double battery_age = (double)(len - 1) * p.dt * 3600;                    // :138  max(End) == len-1
         const double mean_soc_cal = r.mean_sum / (double)m;                            // :140
         if (max_dod > 5) atomicOr(p.err_flags, 4u);                                    // :164-167
@@ -461,6 +484,7 @@ __device__ __forceinline__ double sei_finish(const StepParams& p, size_t i, cons
         p.life[i] = new_l;                                                             // :192
         p.rf_len[i] = m;                                                               // :195
     }
+    PT_MARK(4);
     return deg;
 }
 
@@ -484,6 +508,12 @@ __device__ __forceinline__ double empirical_eval(double dt, double evse, int N, 
     return cal + cyc;
 }
 
+// 8-byte asynchronous global->shared copy (LDGSTS): no register staging, any number in flight per thread
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // --------------------------------------------------------------------------------------- TMA bulk store helpers
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     // make the generic-proxy shared-memory writes visible to the async proxy, then one bulk copy (UBLKCP)
@@ -499,6 +529,12 @@ __device__ __forceinline__ void bulk_store_wait_read() {
 // ------------------------------------------------------------------------------------------------ step kernel
 // Work-list entry pushed by the step kernel for envs that need the post kernel (daily degradation and/or reset).
 constexpr int WL_TRIGGER = 1, WL_RESET = 2;
+// Envs with a degradation evaluation (possibly followed by a reset) and envs that only reset go to separate lists:
+// the first kind is one CTA's worth of cooperative work each, the second a quarter CTA's.
+__device__ __forceinline__ void wl_push(const StepParams& p, int e, int wf) {
+    if (wf & WL_TRIGGER) p.wl[atomicAdd(p.wl_count, 1)] = make_int2(e, wf);
+    else p.wlr[atomicAdd(p.wl_count + 1, 1)] = e;
+}
 
 // Shared-memory layout (dynamic): EnvS envs[B] | double contrib[kNQ][slots] | double sums[kNQ][B] |
 //                                 float obs_tile[B][D] (16-byte aligned)
@@ -764,8 +800,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
             st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, 0), keep);
             const int wf = ((es.flags & EF_TRIGGER) ? WL_TRIGGER : 0) | ((es.flags & EF_RESET) ? WL_RESET : 0);
             if (wf) {   // the post kernel evaluates the degradation first and resets afterwards, like the reference
-                const int slot = atomicAdd(p.wl_count, 1);
-                p.wl[slot] = make_int2(e, wf);
+                wl_push(p, e, wf);
             }
         }
         p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
@@ -940,8 +975,7 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
                 st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, 0), keep);
                 const int wf = ((es.flags & EF_TRIGGER) ? WL_TRIGGER : 0) | ((es.flags & EF_RESET) ? WL_RESET : 0);
                 if (wf) {
-                    const int sl = atomicAdd(p.wl_count, 1);
-                    p.wl[sl] = make_int2(e, wf);
+                    wl_push(p, e, wf);
                 }
                 p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
                 p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
@@ -1373,8 +1407,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) fleet_step_tma_kernel(const Ste
                 p.env4[e] = make_int4(ev_mine.x + 1, ev_mine.y, ev_mine.z, 0);
                 const int wf = ((fl & EF_TRIGGER) ? WL_TRIGGER : 0) | ((fl & EF_RESET) ? WL_RESET : 0);
                 if (wf) {
-                    const int slot = atomicAdd(p.wl_count, 1);
-                    p.wl[slot] = make_int2(e, wf);
+                    wl_push(p, e, wf);
                 }
                 p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
                 p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
@@ -1539,6 +1572,27 @@ __host__ __device__ inline size_t post_smem_bytes(int cap) {
                    (size_t)cap * kPostThreads * 2);
 }
 
+// Auto-reset of one finished env by `nthr` cooperating threads (rank `tid`): FleetEnv.reset as the SubprocVecEnv
+// worker calls it right after a done step.  `ev` is the env's {t, t_start, ep_count} before the reset.
+template <bool kNorm, bool kAux>
+__device__ __forceinline__ void post_reset_env(const StepParams& p, int e, int4 ev, int tid, int nthr) {
+    const int t0 = p.next_start ? p.next_start[e] : draw_start(p.seed, p.start_lo, p.start_hi, p.env_id_offset + e, ev.z);
+    for (int n = tid; n < p.N; n += nthr)
+        reset_slot<kNorm, kAux>(p, e, n, t0, p.obs ? p.obs + (size_t)e * p.D : nullptr, !p.carry);
+    if (tid == 0) {
+        p.env4[e] = make_int4(t0, t0, ev.z + 1, 0);
+        p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = 0;
+    }
+}
+// The last CTA of a post kernel to finish clears both work lists for the next step.
+__device__ __forceinline__ void post_finish_lists(const StepParams& p) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int d = atomicAdd(p.wl_done, 1u);
+        if (d == gridDim.x - 1) { p.wl_count[0] = 0; p.wl_count[1] = 0; p.wl_count[2] = 0; p.wl_count[3] = 0; *p.wl_done = 0; }
+    }
+}
+
 template <bool kNorm, bool kAux>
 __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1552,6 +1606,7 @@ __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepPara
     const int tid = threadIdx.x;
     const int count = *p.wl_count;
 
+    PT_START();
     for (int w = blockIdx.x; w < count; w += gridDim.x) {
         const int2 ent = p.wl[w];
         const int e = ent.x, wf = ent.y;
@@ -1589,25 +1644,301 @@ __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepPara
             __syncthreads();
             if (tid == 0 && s_deg != 0)
                 atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
+            PT_MARK(5);
         }
-        if (wf & WL_RESET) {
-            const int t0 = p.next_start ? p.next_start[e]
-                                        : draw_start(p.seed, p.start_lo, p.start_hi, p.env_id_offset + e, ev.z);
-            for (int n = tid; n < N; n += kPostThreads)
-                reset_slot<kNorm, kAux>(p, e, n, t0, p.obs ? p.obs + (size_t)e * D : nullptr, !p.carry);
-            if (tid == 0) {
-                p.env4[e] = make_int4(t0, t0, ev.z + 1, 0);
-                p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = 0;
+        if (wf & WL_RESET) post_reset_env<kNorm, kAux>(p, e, ev, tid, kPostThreads);
+        PT_MARK(6);
+        __syncthreads();
+    }
+    const int count_r = p.wl_count[1];
+    for (int w = blockIdx.x; w < count_r; w += gridDim.x) {
+        const int e = p.wlr[w];
+        post_reset_env<kNorm, kAux>(p, e, p.env4[e], tid, kPostThreads);
+    }
+    post_finish_lists(p);
+}
+
+// ------------------------------------------------------------------------- cooperative post kernel (default)
+// One CTA of 256 threads per degradation entry, fetched dynamically; the env's whole soc_deg history (len x N float64,
+// contiguous in HBM) is staged once in shared memory, transposed to one column per vehicle (odd pitch: conflict-free
+// both along and across columns), and every phase works on that copy:
+//   A. reversal detection, one WARP per vehicle, 32 samples per step: a sample is a reversal iff the nearest
+//      non-zero differences on either side have a negative product (rainflow.reversals skips plateaus and reports a
+//      plateau's last sample); found with ballots, compacted IN PLACE (values only: nothing downstream needs the
+//      sample indices, the cycle list is positional).
+//   B. the three-point stack, one THREAD per vehicle (inherently serial), vehicles spread over all 8 warps so that few
+//      lanes diverge together; the stack holds reversal ordinals in a full-depth shared-memory column (no overflow
+//      path), the top three values live in registers; cycles are recorded as (ordinal a, ordinal b, full) words.
+//   C. SEI stress of the new cycles (pow/exp per cycle), ALL threads: po_g threads per vehicle take the cycles
+//      round-robin; partial sums are combined in a fixed order (deterministic; differs from the sequential sum in the
+//      last bits only, inside the stated SOH tolerance).
+//   D. per-vehicle fade update, then the env's reset if it also finished.
+// Reset-only entries are taken by quarter CTAs (64 threads) afterwards.
+constexpr int kPost2Threads = 256;
+
+struct Post2Misc {   // per-chunk scalars in shared memory
+    double part[kPost2Threads];
+    double pmax[kPost2Threads];
+};
+
+template <bool kNorm, bool kAux>
+__global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = p.N, LP = p.po_lp, NC = p.po_nc;
+    double* rv = reinterpret_cast<double*>(smem_raw);                      // [NC][LP] samples, then reversal values
+    uint16_t* stk = reinterpret_cast<uint16_t*>(smem_raw + p.po_stk);      // [NC][LP] stack of reversal ordinals
+    uint32_t* recs = reinterpret_cast<uint32_t*>(smem_raw + p.po_recs);    // [NC][LP] cycle records
+    Post2Misc* misc = reinterpret_cast<Post2Misc*>(smem_raw + p.po_misc);
+    int* s_m = reinterpret_cast<int*>(misc + 1);                           // [NC] cycles found
+    int* s_rfl = s_m + NC;                                                 // [NC] rainflow_length of the vehicle
+    double* s_msum = reinterpret_cast<double*>(s_rfl + NC);                // [NC] sum of cycle means (2*NC ints before it)
+    __shared__ int s_w;
+    __shared__ double s_deg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int count_d = p.wl_count[0], count_r = p.wl_count[1];
+    const double alpha_sei = 5.75E-2, beta_sei = 121, k_sigma = 1.04, sigma_ref = 0.5, k_temp = 6.93E-2,
+                 temp_ref = 25, k_dt = 4.14E-10, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
+    PT_START();
+
+    for (;;) {
+        if (tid == 0) { s_w = atomicAdd(p.wl_count + 2, 1); s_deg = 0; }
+        __syncthreads();
+        const int w = s_w;
+        if (w >= count_d) break;
+        const int2 ent = p.wl[w];
+        const int e = ent.x, wf = ent.y;
+        const int4 ev = p.env4[e];                      // {t (already advanced), t_start, ep_count}
+        const int len = ev.x - ev.y + 1;                // history rows 0..k+1 where k+1 = t - t_start
+        const double* hbase = p.hist + (size_t)e * p.R * N;
+
+        if (p.deg_mode == FLEET_DEG_EMPIRICAL) {
+            for (int n = tid; n < N; n += kPost2Threads) {
+                const size_t ii = (size_t)e * N + n;
+                const double deg = empirical_eval(p.dt, p.evse, N, hbase + n, len);
+                p.n_cycles[ii] = 0;
+                p.last_deg[ii] = deg;
+                p.soh[ii] = p.soh[ii] - deg;
+                if (deg != 0) atomicAdd(&s_deg, deg);
+            }
+        } else {
+            for (int n0 = 0; n0 < N; n0 += NC) {
+                const int nc = min(NC, N - n0);
+                // ---- stage the chunk: coalesced along vehicles in HBM, one column per vehicle in shared memory;
+                // 8-byte cp.async copies, all in flight at once (one HBM round trip for the whole history)
+                for (int r = warp; r < len; r += kPost2Threads / 32) {
+                    const double* src = hbase + (size_t)r * N + n0;
+                    for (int c = lane; c < nc; c += 32) cp_async8(rv + c * LP + r, src + c);
+                }
+                // per-vehicle degradation state, needed at the end: fetched under the staging latency
+                double st_fd = 0, st_life = 0, st_soh = 0;
+                int st_rfl = 0;
+                if (tid < nc) {
+                    const size_t ii = (size_t)e * N + n0 + tid;
+                    st_fd = p.fd_cyc[ii]; st_life = p.life[ii]; st_soh = p.soh[ii]; st_rfl = p.rf_len[ii];
+                    s_rfl[tid] = st_rfl;
+                }
+                cp_async_wait_all();
+                __syncthreads();
+                PT_MARK(0);
+
+                // ---- A + B: warp `warp` owns vehicles [warp*cpw, warp*cpw+cpw) of the chunk
+                const int cpw = (nc + 7) >> 3;
+                int my_nr = 0;                                       // lane j keeps the count of the warp's j-th vehicle
+                for (int j = 0; j < cpw; j++) {
+                    const int c = warp * cpw + j;
+                    if (c >= nc) break;                              // warp-uniform
+                    double* col = rv + c * LP;
+                    int nr = 1;                                      // yield (0, x0): col[0] stays where it is
+                    if (len >= 3) {
+                        const double x_end = col[len - 1];
+                        double carry_d = col[1] - col[0];            // d_last before the loop (may be 0)
+                        for (int q0 = 1; q0 <= len - 2; q0 += 32) {
+                            const int q = q0 + lane;
+                            const bool valid = q <= len - 2;
+                            const double xa = valid ? col[q] : 0.0, xb = valid ? col[q + 1] : 0.0;
+                            const double d = xb - xa;
+                            const bool nz = valid && (xb != xa);
+                            const unsigned nzmask = __ballot_sync(0xffffffffu, nz);
+                            const unsigned lower = nzmask & ((1u << lane) - 1u);
+                            const int src = lower ? 31 - __clz(lower) : 0;
+                            const double d_lo = __shfl_sync(0xffffffffu, d, src);
+                            const double d_prev = lower ? d_lo : carry_d;
+                            const bool rev = nz && (d_prev * d < 0);
+                            const unsigned revmask = __ballot_sync(0xffffffffu, rev);
+                            const int top = nzmask ? 31 - __clz(nzmask) : 0;
+                            const double d_top = __shfl_sync(0xffffffffu, d, top);
+                            if (nzmask) carry_d = d_top;
+                            // the ballots above are the barrier between this step's reads and its in-place writes
+                            // (positions < q0 + 32; the next step reads from q0 + 32 on)
+                            if (rev) col[nr + __popc(revmask & ((1u << lane) - 1u))] = xa;
+                            nr += __popc(revmask);
+                        }
+                        if (lane == 0) col[nr] = x_end;              // the last sample closes the series
+                        nr++;
+                    }
+                    if (lane == j) my_nr = nr;
+                }
+                __syncwarp();
+                PT_MARK(1);
+                if (lane < cpw && warp * cpw + lane < nc) {
+                    const int c = warp * cpw + lane;
+                    const double* col = rv + c * LP;
+                    uint16_t* st = stk + c * LP;
+                    uint32_t* rc = recs + c * LP;
+                    const int nr = (len >= 2) ? my_nr : 0;
+                    int lo = 0, hi = 0, m = 0;
+                    double mean_sum = 0;
+                    // the top five stack entries are mirrored in registers (a4/o4 = top; a_k valid iff depth >= 5-k):
+                    // after a cycle closes, the next three-point test runs on registers while the two entries that move
+                    // into the mirror are fetched from shared memory off the critical path
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+                    int o0 = 0, o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+#define RF2_EMIT(oa, xa, ob, xb_, full)                                                       \
+    do {                                                                                      \
+        mean_sum += 0.5 * ((xa) + (xb_));                                                     \
+        rc[m] = (uint32_t)(oa) | ((uint32_t)(ob) << 15) | ((uint32_t)(full) << 30);           \
+        m++;                                                                                  \
+    } while (0)
+                    if (nr >= 2) {
+                        for (int r0 = 0; r0 < nr; r0 += 4) {
+                            double vb[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) vb[u] = col[min(r0 + u, nr - 1)];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int r = r0 + u;
+                                if (r < nr) {
+                                    st[hi] = (uint16_t)r; hi++;
+                                    a0 = a1; o0 = o1; a1 = a2; o1 = o2; a2 = a3; o2 = o3; a3 = a4; o3 = o4; a4 = vb[u]; o4 = r;
+                                    while (hi - lo >= 3) {
+                                        const double X = fabs(a4 - a3), Y = fabs(a3 - a2);
+                                        if (X < Y) break;
+                                        if (hi - lo == 3) { RF2_EMIT(o2, a2, o3, a3, 0); lo++; }
+                                        else {
+                                            RF2_EMIT(o2, a2, o3, a3, 1);
+                                            hi -= 2;
+                                            st[hi - 1] = (uint16_t)o4;
+                                            a3 = a1; o3 = o1; a2 = a0; o2 = o0;
+                                            if (hi - lo >= 4) { o1 = st[hi - 4]; a1 = col[o1]; }
+                                            if (hi - lo >= 5) { o0 = st[hi - 5]; a0 = col[o0]; }
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        for (int k = lo; k + 1 < hi; k++) {
+                            const int oa = st[k], ob = st[k + 1];
+                            RF2_EMIT(oa, col[oa], ob, col[ob], 0);
+                        }
+                    }
+#undef RF2_EMIT
+                    s_m[c] = m;
+                    s_msum[c] = mean_sum;
+                }
+                __syncthreads();
+                PT_MARK(2);
+
+                // ---- C: stress of the cycles in the positional slice [rainflow_length-1 : m-1]  (:146)
+                const double s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
+                {
+                    const int G = p.po_g;
+                    const int c = tid / G, sub = tid - c * G;
+                    double fs = 0, mx = 0;
+                    if (c < nc) {
+                        const int m = s_m[c], rfl = s_rfl[c];
+                        if (m > rfl) {
+                            const double* col = rv + c * LP;
+                            const uint32_t* rc = recs + c * LP;
+                            for (int j = rfl - 1 + sub; j < m - 1; j += G) {
+                                const uint32_t rec = rc[j];
+                                const double xa = col[rec & 0x7fffu], xb = col[(rec >> 15) & 0x7fffu];
+                                const double range = fabs(xa - xb), mean = 0.5 * (xa + xb);
+                                double eff = range * ((rec >> 30) ? 1.0 : 0.5);                        // :170
+                                eff = eff < 0 ? 0 : (eff > 1 ? 1 : eff);
+                                const double s_dod = 1.0 / (kd1 * pow(eff, kd2) + kd3);                // :68
+                                const double s_soc = exp(k_sigma * (mean - sigma_ref));                // :70
+                                fs += s_dod * s_soc * s_temp;                                          // :77-79
+                                if (range > mx) mx = range;
+                            }
+                        }
+                    }
+                    misc->part[tid] = fs;
+                    misc->pmax[tid] = mx;
+                }
+                __syncthreads();
+                PT_MARK(3);
+
+                // ---- D: capacity fade of each vehicle (rainflow_sei_degradation.py:128-206); thread c = vehicle c
+                {
+                    double deg = 0;
+                    if (tid < nc) {
+                        const int c = tid;
+                        const size_t ii = (size_t)e * N + n0 + c;
+                        const int m = s_m[c], rfl = st_rfl;
+                        const int G = p.po_g;
+                        p.n_cycles[ii] = m;
+                        if (m > rfl) {                                                                     // :143
+                            double fsum = 0, max_dod = 0;
+                            for (int g = 0; g < G; g++) {
+                                fsum += misc->part[c * G + g];
+                                max_dod = fmax(max_dod, misc->pmax[c * G + g]);
+                            }
+                            const double battery_age = (double)(len - 1) * p.dt * 3600;                    // :138
+                            const double mean_soc_cal = s_msum[c] / (double)m;                             // :140
+                            if (max_dod > 5) atomicOr(p.err_flags, 4u);                                    // :164-167
+                            const double fd_cal = (k_dt * battery_age) * exp(k_sigma * (mean_soc_cal - sigma_ref)) * s_temp;  // :81-83
+                            const double fd_cyc = st_fd + fsum;                                            // :174
+                            p.fd_cyc[ii] = fd_cyc;
+                            const double fd = fd_cyc + fd_cal;
+                            const double l_old = st_life;
+                            double new_l;
+                            if (p.init_soh == 1.0) {
+                                new_l = 1 - alpha_sei * exp(-beta_sei * fd) - (1 - alpha_sei) * exp(-fd);  // :85-86
+                                if (new_l < 0) atomicOr(p.err_flags, 2u);                                  // :179-180
+                            } else {
+                                new_l = 1 - (1 - l_old) * exp(-fd);                                        // :89,186
+                            }
+                            deg = new_l - l_old;                                                           // :189
+                            p.life[ii] = new_l;                                                            // :192
+                            p.rf_len[ii] = m;                                                              // :195
+                        }
+                        p.last_deg[ii] = deg;
+                        p.soh[ii] = st_soh - deg;                                                          // :671
+                    }
+                    if (warp * 32 < nc) {                            // warp-uniform: fixed-order tree, one atomic per warp
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) deg += __shfl_xor_sync(0xffffffffu, deg, off);
+                        if (lane == 0 && deg != 0) atomicAdd(&s_deg, deg);
+                    }
+                }
+                __syncthreads();                                     // the chunk's shared memory is reused
+                PT_MARK(4);
             }
         }
         __syncthreads();
+        if (tid == 0 && s_deg != 0)
+            atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
+        if (wf & WL_RESET) post_reset_env<kNorm, kAux>(p, e, ev, tid, kPost2Threads);
+        __syncthreads();                                             // s_w / s_deg are rewritten by thread 0
+        PT_MARK(5);
     }
-    // the last CTA to finish clears the work list for the next step
-    if (tid == 0) {
-        __threadfence();
-        const unsigned int d = atomicAdd(p.wl_done, 1u);
-        if (d == gridDim.x - 1) { *p.wl_count = 0; *p.wl_done = 0; }
+
+    // ---- reset-only entries: a quarter CTA (64 threads) per env
+    {
+        const int grp = tid >> 6, gt = tid & 63;
+        for (;;) {
+            __syncthreads();
+            if (tid == 0) s_w = atomicAdd(p.wl_count + 3, 4);
+            __syncthreads();
+            const int w = s_w + grp;
+            if (s_w >= count_r) break;
+            if (w < count_r) {
+                const int e = p.wlr[w];
+                post_reset_env<kNorm, kAux>(p, e, p.env4[e], gt, 64);
+            }
+        }
     }
+    post_finish_lists(p);
 }
 
 template <bool kNorm, bool kAux>
@@ -1709,6 +2040,8 @@ struct FleetHandle {
     size_t smem_step = 0, smem_post = 0, smem_tma = 0, smem_pf = 0;
     int grid_pf = 0, use_pf = 0;
     int grid = 0, grid_post = 0, need_post = 0, num_sms = 0, grid_tma = 0, use_tma = 0;
+    int use_post2 = 0, grid_post2 = 0;
+    size_t smem_post2 = 0;
     int max_smem_optin = 0;
     // host-call staging (fleet_step_host)
     float* h_actions_dev = nullptr; float* h_obs_dev = nullptr; float* h_reward_dev = nullptr; uint8_t* h_done_dev = nullptr;
@@ -1786,6 +2119,10 @@ StepKernel pick_post(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_post_kernel<true, true> : fleet_post_kernel<true, false>;
     return h->c.aux ? fleet_post_kernel<false, true> : fleet_post_kernel<false, false>;
 }
+StepKernel pick_post2(const FleetHandle* h) {
+    if (h->c.normalize) return h->c.aux ? fleet_post2_kernel<true, true> : fleet_post2_kernel<true, false>;
+    return h->c.aux ? fleet_post2_kernel<false, true> : fleet_post2_kernel<false, false>;
+}
 StepKernel pick_reset(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_reset_kernel<true, true> : fleet_reset_kernel<true, false>;
     return h->c.aux ? fleet_reset_kernel<false, true> : fleet_reset_kernel<false, false>;
@@ -1807,6 +2144,14 @@ int fleet_obs_dim(const FleetHandle* h) { return h ? h->D : FLEET_E_INVALID; }
 int fleet_num_evs(const FleetHandle* h) { return h ? h->N : FLEET_E_INVALID; }
 int fleet_num_envs(const FleetHandle* h) { return h ? h->E : FLEET_E_INVALID; }
 int64_t fleet_launch_count(const FleetHandle* h) { return h ? h->launches : 0; }
+#ifdef POST_TIMING
+int32_t fleet_debug_post_clk(unsigned long long* out, int32_t reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_post_clk, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_post_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif
 int64_t fleet_device_bytes(const FleetHandle* h) { return h ? h->bytes : 0; }
 
 int fleet_destroy(FleetHandle* h) {
@@ -1987,6 +2332,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     if ((rc = dev_alloc(h, &p.stats, (size_t)kStatStripes * FLEET_S__COUNT))) return rc;
     if ((rc = dev_alloc(h, &p.err_flags, (size_t)4))) return rc;
     if ((rc = dev_alloc(h, &p.wl, (size_t)E))) return rc;
+    if ((rc = dev_alloc(h, &p.wlr, (size_t)E))) return rc;
     if ((rc = dev_alloc(h, &p.wl_count, (size_t)4))) return rc;
     if ((rc = dev_alloc(h, &p.wl_done, (size_t)4))) return rc;
 
@@ -2055,6 +2401,35 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
         p.scratch_cap = sc;
         if ((rc = dev_alloc(h, &p.post_scratch_v, (size_t)h->grid_post * sc * kPostThreads, false))) return rc;
         if ((rc = dev_alloc(h, &p.post_scratch_i, (size_t)h->grid_post * sc * kPostThreads, false))) return rc;
+    }
+    // cooperative post kernel (default): the env's history staged in shared memory, NC vehicles at a time
+    {
+        const char* force = getenv("FLEETSTEP_POST");     // "v1": the thread-per-vehicle kernel
+        const int R = c.episode_steps + 1;
+        const int LP = R | 1;                             // odd column pitch
+        const size_t per_vehicle = (size_t)LP * 14 + 16;  // values 8 + ordinals 2 + records 4 per row; 16 B of scalars
+        const size_t fixed = sizeof(Post2Misc) + 64;
+        auto fit = [&](size_t budget) { return budget > fixed ? (int64_t)((budget - fixed) / per_vehicle) : 0; };
+        int64_t nc = fit((size_t)(h->max_smem_optin + 1024) / 3 - 1024 - 1024);   // three CTAs per SM
+        if (nc < (N < 8 ? N : 8)) nc = fit((size_t)h->max_smem_optin);
+        if (nc > N) nc = N;
+        if (nc > kPost2Threads) nc = kPost2Threads;
+        const bool sei = c.calc_degradation && c.deg_mode == FLEET_DEG_SEI;
+        if ((!force || strcmp(force, "v1") != 0) && h->need_post && (nc >= 1 || !sei)) {
+            if (!sei) nc = 1;
+            p.po_nc = (int)nc; p.po_lp = LP; p.po_g = kPost2Threads / (int)nc;
+            p.po_stk = (int)align16((size_t)nc * LP * 8);
+            p.po_recs = (int)align16((size_t)p.po_stk + (size_t)nc * LP * 2);
+            p.po_misc = (int)align16((size_t)p.po_recs + (size_t)nc * LP * 4);
+            h->smem_post2 = align16((size_t)p.po_misc + sizeof(Post2Misc) + (size_t)(2 * nc + 2) * 4 + (size_t)nc * 8);
+            int per_sm = 1;
+            CUDA_TRY(h, cudaFuncSetAttribute(pick_post2(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post2));
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post2(h), kPost2Threads, h->smem_post2));
+            if (per_sm < 1) per_sm = 1;
+            const int64_t g = (int64_t)h->num_sms * per_sm;
+            h->grid_post2 = (int)(g < E ? g : E);
+            h->use_post2 = 1;
+        }
     }
     h->smem_step = sm;
     // persistent prefetching kernel (default where applicable)
@@ -2145,7 +2520,8 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     else pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
     h->launches++;
     if (h->need_post) {   // daily degradation, then auto-reset, for the envs the step kernel put on the work list
-        pick_post(h)<<<h->grid_post, kPostThreads, h->smem_post, (cudaStream_t)stream>>>(p);
+        if (h->use_post2) pick_post2(h)<<<h->grid_post2, kPost2Threads, h->smem_post2, (cudaStream_t)stream>>>(p);
+        else pick_post(h)<<<h->grid_post, kPostThreads, h->smem_post, (cudaStream_t)stream>>>(p);
         h->launches++;
     }
     cudaError_t e = cudaGetLastError();

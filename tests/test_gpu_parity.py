@@ -40,13 +40,20 @@ CASES = {
 # TMA kernel (FLEETSTEP_KERNEL=tma; needs auto-reset, even 7 <= N <= 224, D % 4 == 0)
 KERNELS = ([(n, "pf") for n in sorted(CASES) if CASES[n]["n_evs"] >= 8 and CASES[n]["n_evs"] <= 256
             and CASES[n].get("over", {}).get("auto_reset", 1)]
-           + [(n, "generic") for n in sorted(CASES)] + [(n, "tma") for n in ("lmd_50ev_e36", "ut_10ev_e50")])
+           + [(n, "generic") for n in sorted(CASES)] + [(n, "tma") for n in ("lmd_50ev_e36", "ut_10ev_e50")]
+           # the thread-per-vehicle post kernel (FLEETSTEP_POST=v1) that the cooperative one falls back to
+           + [(n, "generic+postv1") for n in ("lmd_50ev", "ct_20ev_two_trips", "lmd_300ev", "lmd_9ev_norm_nocarry",
+                                              "lmd_1ev")])
 
 
 @pytest.mark.parametrize("name,kernel", KERNELS)
 def test_gpu_vs_oracle(name, kernel, monkeypatch):
     from fleetrl_b200._lib import FleetStepHandle
-    monkeypatch.setenv("FLEETSTEP_KERNEL", kernel)
+    monkeypatch.setenv("FLEETSTEP_KERNEL", kernel.split("+")[0])
+    if kernel.endswith("+postv1"):
+        monkeypatch.setenv("FLEETSTEP_POST", "v1")
+    else:
+        monkeypatch.delenv("FLEETSTEP_POST", raising=False)
 
     cs = dict(CASES[name])
     E, steps = cs.pop("E"), cs.pop("steps")
@@ -82,7 +89,8 @@ def test_gpu_vs_oracle(name, kernel, monkeypatch):
 
     exact = ["time_idx", "finish_idx", "hours_left", "target_soc", "rf_len", "n_cycles", "ep_count"]
     # SOC / soc_deg are bit-exact for a given SOH.  Once a vehicle has been through a daily SEI evaluation its SOH agrees
-    # with the oracle to 1e-13 only (device pow/exp vs libm), so its capacity and hence its SOC may differ in the last
+    # with the oracle to 1e-13 only (device pow/exp vs libm, and the cooperative post kernel adds a vehicle's cycle
+    # stress terms in a fixed but not sequential order), so its capacity and hence its SOC may differ in the last
     # bit: exact equality is asserted where degradation cannot interfere, the stated 1e-12 otherwise.
     soc_exact = (not consts.calc_degradation) or consts.deg_mode == 1
     n_done = 0
@@ -104,7 +112,7 @@ def test_gpu_vs_oracle(name, kernel, monkeypatch):
                 np.testing.assert_array_equal(g_v, o_v, err_msg=f"{k} step {s}")
             else:
                 np.testing.assert_allclose(g_v, o_v, rtol=0, atol=1e-12, err_msg=f"{k} step {s}")
-                assert (g_v != o_v).mean() < 2e-3, f"{k} step {s}: too many non-identical elements"
+                assert (g_v != o_v).mean() < 1e-2, f"{k} step {s}: too many non-identical elements"
         np.testing.assert_allclose(gpu.get("reward64").cpu().numpy(), o_rew, rtol=1e-11, atol=1e-10, err_msg=f"reward step {s}")
         np.testing.assert_allclose(gpu.get("cashflow").cpu().numpy(), o_cash, rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(rew.cpu().numpy(), o_rew.astype(np.float32), rtol=1e-6, atol=1e-6)
