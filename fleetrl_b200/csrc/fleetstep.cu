@@ -840,13 +840,47 @@ __host__ __device__ inline size_t pf_smem_bytes(int B, int N, int D) {
                    2 * align16((size_t)B * D * 4));
 }
 
-// named barriers: id 0 is __syncthreads
-__device__ __forceinline__ void nbar_sync(int id) { asm volatile("bar.sync %0, %1;" :: "r"(id), "n"(kPfThreads) : "memory"); }
-__device__ __forceinline__ void nbar_arrive(int id) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "n"(kPfThreads) : "memory"); }
-constexpr int kBarDone = 1;   // +buf (2): compute -> epilogue: tile written (contributions, obs tile)
-constexpr int kBarFree = 3;   // +buf (2): epilogue -> compute: contribution + obs buffers may be reused
-constexpr int kBarEnv = 5;    // +ebuf (3): epilogue -> compute: env scratch of the tile is staged
-
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait suspends the thread for a hardware-defined time before returning false (a __nanosleep back-off here
+    // was measured to be 2.4x slower: the hand-offs are on the critical path)
+    while (!mbar_try_wait(bar, parity)) { }
+}
+// pf kernel hand-offs are mbarriers (not named barriers): a waiting warp then depends only on the producer of what it
+// waits for, never on its sibling compute warps, so the eight compute warps drift apart by up to a tile and their
+// per-tile imbalance (charging / discharging / absent vehicles) averages out instead of adding up.
+#ifdef PF_TIMING
+__device__ unsigned long long g_pf_clk[16];
+#define PF_MARK(k) do { const long long _c = clock64(); _acc[(k) & 7] += (unsigned long long)(_c - _pt); _pt = _c; } while (0)
+#define PF_START() long long _pt = clock64()
+#define PF_SETTLE() do { int _d; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(_d) : "r"((uint32_t)__cvta_generic_to_shared(smem_raw)) : "memory"); if (_d == 0x7fffffff) _acc[7]++; } while (0)
+#define PF_DECL() unsigned long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PF_FLUSH(base) do { if ((threadIdx.x & 31) == 0) { for (int _k = 0; _k < 8; _k++) if (_acc[_k]) atomicAdd(&g_pf_clk[(base) + _k], _acc[_k]); } } while (0)
+#else
+#define PF_MARK(k) do {} while (0)
+#define PF_START() do {} while (0)
+#define PF_SETTLE() do {} while (0)
+#define PF_DECL() do {} while (0)
+#define PF_FLUSH(base) do {} while (0)
+#endif
 template <bool kNorm, bool kAux>
 __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -864,6 +898,16 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
     const int H = p.Ha + p.Hb;
     const uint64_t keep = l2_evict_last_policy();
     const int tile0 = blockIdx.x, G = gridDim.x;
+
+    // done[buf]: compute -> epilogue, tile written (all compute threads arrive); freeb[buf]: epilogue -> compute,
+    // contribution + obs buffers may be reused; envb[ebuf]: epilogue -> compute, env scratch of the tile is staged
+    __shared__ uint64_t bar_done[2], bar_free[2], bar_env[3];
+    if (tid == 0) {
+        mbar_init(&bar_done[0], kPfCompute); mbar_init(&bar_done[1], kPfCompute);
+        mbar_init(&bar_free[0], 1); mbar_init(&bar_free[1], 1);
+        mbar_init(&bar_env[0], 1); mbar_init(&bar_env[1], 1); mbar_init(&bar_env[2], 1);
+    }
+    __syncthreads();
 
     if (tid >= kPfCompute) {
         // =================================================================== epilogue warp
@@ -895,10 +939,12 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
             }
         };
         // env scratch of the first two tiles
-        load_env(tile0); stage_env(tile0, 0); __syncwarp(); nbar_arrive(kBarEnv + 0);
-        load_env(tile0 + G); stage_env(tile0 + G, 1); __syncwarp(); nbar_arrive(kBarEnv + 1);
+        load_env(tile0); stage_env(tile0, 0); __syncwarp(); if (lane == 0) mbar_arrive(&bar_env[0]);
+        load_env(tile0 + G); stage_env(tile0 + G, 1); __syncwarp(); if (lane == 0) mbar_arrive(&bar_env[1]);
 
         int it = 0;
+        PF_DECL();
+        PF_START();
         for (int tile = tile0; tile < ntiles; tile += G, it++) {
             const int buf = it & 1;
             const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % 3) * envs_b);
@@ -910,12 +956,16 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
             load_env(tile + 2 * G);                           // in flight during this epilogue
             double ep_prev = 0;                               // episode return so far (lane < nb), fetched ahead of its use
             if (lane < nb) ep_prev = p.env_f64[(size_t)EF_EP_RETURN * p.E + e0 + lane];
-            nbar_sync(kBarDone + buf);                        // the compute warps have written tile `tile`
+            PF_MARK(0);
+            mbar_wait(&bar_done[buf], (uint32_t)((it >> 1) & 1));   // the compute warps have written tile `tile`
+            PF_SETTLE();
+            PF_MARK(1);
 
             // ---- observation tile -> HBM
             bool any_reset = false;
             for (int bb = 0; bb < nb; bb++) any_reset |= (envs[bb].flags & EF_RESET) != 0;
             const bool use_bulk = p.bulk_ok && nb == B && !any_reset && p.obs != nullptr;
+            PF_MARK(7);
             if (use_bulk) {
                 if (lane == 0) bulk_store_s2g(p.obs + (size_t)e0 * D, obs_tile, (uint32_t)(B * D * 4));
             } else {
@@ -927,6 +977,7 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
                     if (dst) dst[w - bb * D] = obs_tile[w];
                 }
             }
+            PF_MARK(6);
             // ---- per-env sums: one lane per (quantity, env), sequential in car order (deterministic)
             for (int w = lane; w < kNQ * nb; w += 32) {
                 const int q = w / nb, bb = w - q * nb;
@@ -936,12 +987,17 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
                 for (int nn = 0; nn < N; nn++) sum += c[nn];
                 sums[q * B + bb] = sum;
             }
+            PF_MARK(2);
             if (use_bulk && lane == 0) bulk_store_wait_read();
             __syncwarp();
+            PF_MARK(3);
             stage_env(tile + 2 * G, (it + 2) % 3);
             __syncwarp();
-            nbar_arrive(kBarEnv + (it + 2) % 3);
-            nbar_arrive(kBarFree + buf);                      // contribution + obs buffers of this tile are free again
+            if (lane == 0) {
+                mbar_arrive(&bar_env[(it + 2) % 3]);
+                mbar_arrive(&bar_free[buf]);                  // contribution + obs buffers of this tile are free again
+            }
+            PF_MARK(4);
 
             // ---- env-level finalisation: one lane per env
             for (int bb = lane; bb < nb; bb += 32) {
@@ -985,7 +1041,9 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
                 if (p.done) p.done[e] = (uint8_t)dn;
             }
             __syncwarp();   // sums[] is reused by the next tile
+            PF_MARK(5);
         }
+        PF_FLUSH(0);
         if (lane == 0) bulk_store_wait_read();
         return;
     }
@@ -1034,6 +1092,8 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
     }
 
     int it = 0;
+    PF_DECL();
+    PF_START();
     for (int tile = tile0; tile < ntiles; tile += G, it++) {
         const int buf = it & 1;
         const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % 3) * envs_b);
@@ -1046,9 +1106,13 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
         // ---- loads of the next tile go in flight; env4 two tiles ahead
         issue_loads(tile + G, ev1, nxt);
         const int2 ev2 = load_env2(tile + 2 * G);
-
-        nbar_sync(kBarEnv + it % 3);                          // env scratch of this tile is staged
-        if (it >= 2) nbar_sync(kBarFree + buf);               // contribution + obs buffers are free again
+        PF_MARK(4);
+        mbar_wait(&bar_env[it % 3], (uint32_t)((it / 3) & 1));       // env scratch of this tile is staged
+        PF_SETTLE();
+        PF_MARK(0);
+        if (it >= 2) mbar_wait(&bar_free[buf], (uint32_t)(((it >> 1) - 1) & 1));   // contribution + obs buffers are free again
+        PF_SETTLE();
+        PF_MARK(2);
 
         if (active) {
             const PfEnv& es = envs[b];
@@ -1144,10 +1208,12 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
                     ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + q, keep);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (bulk store)
-        nbar_arrive(kBarDone + buf);
+        mbar_arrive(&bar_done[buf]);
+        PF_MARK(3);
         cur = nxt;
         ev1 = ev2;
     }
+    PF_FLUSH(8);
 }
 
 // ------------------------------------------------------------------------------------- persistent TMA step kernel
@@ -1174,30 +1240,6 @@ constexpr int kWsCompute = kWsComputeWarps * 32;       // 224 compute threads
 constexpr int kWsThreads = kWsCompute + 32;            // + manager warp
 constexpr int kWsStages = 2;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    // try_wait suspends the thread for a hardware-defined time before returning false (a __nanosleep back-off here
-    // was measured to be 2.4x slower: the hand-offs are on the critical path)
-    while (!mbar_try_wait(bar, parity)) { }
-}
 __device__ __forceinline__ void tma_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -2144,6 +2186,14 @@ int fleet_obs_dim(const FleetHandle* h) { return h ? h->D : FLEET_E_INVALID; }
 int fleet_num_evs(const FleetHandle* h) { return h ? h->N : FLEET_E_INVALID; }
 int fleet_num_envs(const FleetHandle* h) { return h ? h->E : FLEET_E_INVALID; }
 int64_t fleet_launch_count(const FleetHandle* h) { return h ? h->launches : 0; }
+#ifdef PF_TIMING
+int32_t fleet_debug_pf_clk(unsigned long long* out, int32_t reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_pf_clk, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_pf_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif
 #ifdef POST_TIMING
 int32_t fleet_debug_post_clk(unsigned long long* out, int32_t reset) {
     cudaDeviceSynchronize();
