@@ -128,6 +128,10 @@ struct StepParams {
     int* wlr;                 // [E] work list of the post kernel, reset-only entries: env
     int* wl_count;            // [4] {degradation entries, reset-only entries, next degradation entry, next reset entry}
     unsigned int* wl_done;    // [1]
+    // persistent step kernel geometry (host-computed so that the kernel reads it from the constant bank, not registers)
+    int pf_ntiles, pf_cslots, pf_cper, pf_pair;
+    int pf_envs_b, pf_contrib_b, pf_obs_b;                    // bytes of one env-scratch / contribution / obs buffer
+    int pf_off_contrib, pf_off_sums, pf_off_obs, pf_off_stage;   // shared-memory offsets
     int po_nc, po_lp, po_g;   // cooperative post kernel: vehicles per chunk, column pitch (odd), threads per vehicle in pass 2
     int po_stk, po_recs, po_misc;   // its shared-memory offsets (bytes)
     double* post_scratch_v;   // [grid_post][scratch_cap][64] fallback rainflow value ring
@@ -513,11 +517,34 @@ __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(kPending) : "memory"); }
+// the same with an L2 cache policy (createpolicy): evict_first for streamed state, evict_last for the tables
+__device__ __forceinline__ void cp_async4_hint(uint32_t sdst, const void* gsrc, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" :: "r"(sdst), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async8_hint(uint32_t sdst, const void* gsrc, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" :: "r"(sdst), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t sdst, const void* gsrc, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(sdst), "l"(gsrc), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 
 // --------------------------------------------------------------------------------------- TMA bulk store helpers
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     // make the generic-proxy shared-memory writes visible to the async proxy, then one bulk copy (UBLKCP)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_s2g_nofence(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -828,16 +855,31 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
 //    double-buffered contribution + observation tiles and triple-buffered env scratch.
 // Selected when auto_reset is on and 8 <= N <= 256 (one pass per tile); otherwise the generic kernel runs.
 constexpr int kPfCompute = 256;
-constexpr int kPfThreads = kPfCompute + 32;
+constexpr int kPfThreads = kPfCompute + 64;     // + two epilogue warps
 
 struct PfEnv {   // per-env scratch of a tile (shared memory, triple buffered)
     int t, t_start, ep_count, flags;
     double S, F_cr, F_dr, Rfac, pv_share, gml, pvv;
 };
 
+// input stage of the pf kernel: the per-slot inputs of one tile, structure of arrays indexed by the slot's thread
+constexpr int kPfStA32 = 0, kPfStHl = 1024, kPfStHv = 2048, kPfStSoc = 3072, kPfStSoh = 5120, kPfStSdeg = 7168,
+              kPfStR0 = 9216, kPfStR1 = 13312, kPfStageBytes = 17408, kPfStages = 2;
+// measured on B200 at cfg2: 2 CTAs/SM x 10 warps with ~100 registers (no spills, L1 left for the tables) beat 3 CTAs/SM
+// at 64 registers by 5-6 %
+#ifndef KPFOUT
+#define KPFOUT 3
+#endif
+#ifndef KPFCTAS
+#define KPFCTAS 2
+#endif
+constexpr int kPfOut = KPFOUT;     // output buffers (contributions + obs tile): the epilogue may lag two tiles behind
+constexpr int kPfEnvs = 4;    // env-scratch buffers: staged three tiles ahead
+// Even N: neighbouring vehicles' contributions are added in the compute warp (one shuffle), halving the buffer.
+__host__ __device__ inline int pf_contrib_slots(int B, int N) { return (N & 1) ? B * N : (B * N) / 2; }
 __host__ __device__ inline size_t pf_smem_bytes(int B, int N, int D) {
-    return align16(3 * align16((size_t)B * sizeof(PfEnv)) + 2 * align16((size_t)kNQ * B * N * 8) + align16((size_t)kNQ * B * 8) +
-                   2 * align16((size_t)B * D * 4));
+    return align16(kPfEnvs * align16((size_t)B * sizeof(PfEnv)) + kPfOut * align16((size_t)kNQ * pf_contrib_slots(B, N) * 8) +
+                   2 * align16((size_t)kNQ * B * 8) + kPfOut * align16((size_t)B * D * 4)) + (size_t)kPfStages * kPfStageBytes;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
@@ -882,92 +924,64 @@ __device__ unsigned long long g_pf_clk[16];
 #define PF_FLUSH(base) do {} while (0)
 #endif
 template <bool kNorm, bool kAux>
-__global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N, B = p.B, D = p.D;
     const int cstride = B * N;
-    const size_t envs_b = align16((size_t)B * sizeof(PfEnv)), contrib_b = align16((size_t)kNQ * cstride * 8);
-    const size_t sums_b = align16((size_t)kNQ * B * 8), obs_b = align16((size_t)B * D * 4);
+    const bool pair = p.pf_pair != 0;                        // contributions of vehicle pairs are pre-added (even N)
+    const int cslots = p.pf_cslots;                          // contribution entries per quantity and tile
+    const int cper = p.pf_cper;                              // ... per env
     unsigned char* envs0 = smem_raw;
-    unsigned char* contrib0 = smem_raw + 3 * envs_b;
-    double* sums = reinterpret_cast<double*>(contrib0 + 2 * contrib_b);
-    unsigned char* obs0 = reinterpret_cast<unsigned char*>(sums) + sums_b;
+    unsigned char* contrib0 = smem_raw + p.pf_off_contrib;
+    double* sums = reinterpret_cast<double*>(smem_raw + p.pf_off_sums);
+    unsigned char* obs0 = smem_raw + p.pf_off_obs;
 
     const int tid = threadIdx.x;
-    const int ntiles = (p.E + B - 1) / B;
+    const int ntiles = p.pf_ntiles;
     const int H = p.Ha + p.Hb;
     const uint64_t keep = l2_evict_last_policy();
     const int tile0 = blockIdx.x, G = gridDim.x;
 
     // done[buf]: compute -> epilogue, tile written (all compute threads arrive); freeb[buf]: epilogue -> compute,
     // contribution + obs buffers may be reused; envb[ebuf]: epilogue -> compute, env scratch of the tile is staged
-    __shared__ uint64_t bar_done[2], bar_free[2], bar_env[3];
+    // sums_ready / sums_free[sbuf]: hand-off of the per-env sums between the two epilogue warps
+    __shared__ uint64_t bar_done[kPfOut], bar_free[kPfOut], bar_env[kPfEnvs], bar_sums_ready[2], bar_sums_free[2];
+    __shared__ int s_have_flips, s_any_reset[kPfEnvs];
     if (tid == 0) {
-        mbar_init(&bar_done[0], kPfCompute); mbar_init(&bar_done[1], kPfCompute);
-        mbar_init(&bar_free[0], 1); mbar_init(&bar_free[1], 1);
-        mbar_init(&bar_env[0], 1); mbar_init(&bar_env[1], 1); mbar_init(&bar_env[2], 1);
+        for (int q = 0; q < kPfOut; q++) { mbar_init(&bar_done[q], kPfCompute); mbar_init(&bar_free[q], 1); }
+        for (int q = 0; q < kPfEnvs; q++) mbar_init(&bar_env[q], 1);
+        for (int q = 0; q < 2; q++) { mbar_init(&bar_sums_ready[q], 1); mbar_init(&bar_sums_free[q], 1); }
+        s_have_flips = (*p.n_flips != 0);
     }
     __syncthreads();
 
-    if (tid >= kPfCompute) {
-        // =================================================================== epilogue warp
-        const int lane = tid - kPfCompute;
-        int4 envA = make_int4(0, 0, 0, 0), r0, r1, r2, r3;
-        r0 = r1 = r2 = r3 = make_int4(0, 0, 0, 0);
-        auto load_env = [&](int tile) {                       // lane < B: env4 + step_row[t] of env tile*B + lane
-            const int e = tile * B + lane;
-            if (lane < B && tile < ntiles && e < p.E) {
-                envA = ld_keep_v4(p.env4 + e, keep);
-                const int4* r = reinterpret_cast<const int4*>(p.step_row + min(envA.x, p.T - 2));
-                r0 = ld_keep_v4(r, keep); r1 = ld_keep_v4(r + 1, keep); r2 = ld_keep_v4(r + 2, keep); r3 = ld_keep_v4(r + 3, keep);
-            }
-        };
-        auto stage_env = [&](int tile, int ebuf) {
-            const int e = tile * B + lane;
-            if (lane < B && tile < ntiles && e < p.E) {
-                PfEnv& es = reinterpret_cast<PfEnv*>(envs0 + ebuf * envs_b)[lane];
-                es.t = envA.x; es.t_start = envA.y; es.ep_count = envA.z;
-                int fl = 0;
-                if (envA.x + 1 == envA.y + p.L) fl |= EF_DONE | EF_RESET;
-                if (((uint32_t)r3.w & TF_TRIGGER) && p.calc_deg) fl |= EF_TRIGGER;
-                if ((uint32_t)r3.w & TF_LUNCH) fl |= EF_LUNCH;
-                es.flags = fl;
-                es.S = __hiloint2double(r0.y, r0.x); es.F_cr = __hiloint2double(r0.w, r0.z);
-                es.F_dr = __hiloint2double(r1.y, r1.x); es.Rfac = __hiloint2double(r1.w, r1.z);
-                es.pv_share = __hiloint2double(r2.y, r2.x); es.gml = __hiloint2double(r2.w, r2.z);
-                es.pvv = __hiloint2double(r3.y, r3.x);
-            }
-        };
-        // env scratch of the first two tiles
-        load_env(tile0); stage_env(tile0, 0); __syncwarp(); if (lane == 0) mbar_arrive(&bar_env[0]);
-        load_env(tile0 + G); stage_env(tile0 + G, 1); __syncwarp(); if (lane == 0) mbar_arrive(&bar_env[1]);
-
+    const int sums_stride = (int)align16((size_t)kNQ * B * 8) / 8;   // doubles per sums buffer
+    if (tid >= kPfCompute + 32) {
+        // =================================================================== epilogue warp 1: tile -> HBM, per-env sums
+        // The latency chain between a finished tile and the release of its buffers: bulk store of the observation tile,
+        // the per-env sums (handed to warp 0 through sums[sbuf]), read-completion of the bulk store.
+        const int lane = tid - kPfCompute - 32;
         int it = 0;
         PF_DECL();
         PF_START();
         for (int tile = tile0; tile < ntiles; tile += G, it++) {
-            const int buf = it & 1;
-            const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % 3) * envs_b);
-            const double* contrib = reinterpret_cast<const double*>(contrib0 + buf * contrib_b);
-            const float* obs_tile = reinterpret_cast<const float*>(obs0 + buf * obs_b);
+            const int buf = it % kPfOut, sbuf = it & 1;
+            const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % kPfEnvs) * p.pf_envs_b);
+            const double* contrib = reinterpret_cast<const double*>(contrib0 + buf * p.pf_contrib_b);
+            const float* obs_tile = reinterpret_cast<const float*>(obs0 + buf * p.pf_obs_b);
+            double* sums_w = sums + sbuf * sums_stride;
             const int e0 = tile * B;
             const int nb = min(B, p.E - e0);
-
-            load_env(tile + 2 * G);                           // in flight during this epilogue
-            double ep_prev = 0;                               // episode return so far (lane < nb), fetched ahead of its use
-            if (lane < nb) ep_prev = p.env_f64[(size_t)EF_EP_RETURN * p.E + e0 + lane];
             PF_MARK(0);
-            mbar_wait(&bar_done[buf], (uint32_t)((it >> 1) & 1));   // the compute warps have written tile `tile`
+            mbar_wait(&bar_done[buf], (uint32_t)((it / kPfOut) & 1));   // the compute warps have written tile `tile`
             PF_SETTLE();
             PF_MARK(1);
 
             // ---- observation tile -> HBM
-            bool any_reset = false;
-            for (int bb = 0; bb < nb; bb++) any_reset |= (envs[bb].flags & EF_RESET) != 0;
-            const bool use_bulk = p.bulk_ok && nb == B && !any_reset && p.obs != nullptr;
-            PF_MARK(7);
+            const bool use_bulk = p.bulk_ok && nb == B && !s_any_reset[it % kPfEnvs] && p.obs != nullptr;
             if (use_bulk) {
-                if (lane == 0) bulk_store_s2g(p.obs + (size_t)e0 * D, obs_tile, (uint32_t)(B * D * 4));
+                // the writers have run fence.proxy.async before arriving on bar_done: no second fence here
+                if (lane == 0) bulk_store_s2g_nofence(p.obs + (size_t)e0 * D, obs_tile, (uint32_t)(B * D * 4));
             } else {
                 for (int w = lane; w < nb * D; w += 32) {
                     const int bb = w / D;
@@ -978,35 +992,105 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
                 }
             }
             PF_MARK(6);
-            // ---- per-env sums: one lane per (quantity, env), sequential in car order (deterministic)
+            // ---- per-env sums: one lane per (quantity, env); five interleaved partial sums in car order, combined in
+            // a fixed order (deterministic run to run; the dependent-add chain is 5x shorter than a sequential sum)
+            if (it >= 2) mbar_wait(&bar_sums_free[sbuf], (uint32_t)(((it >> 1) - 1) & 1));
             for (int w = lane; w < kNQ * nb; w += 32) {
                 const int q = w / nb, bb = w - q * nb;
-                const double* c = contrib + q * cstride + bb * N;
-                double sum = 0;
-#pragma unroll 10
-                for (int nn = 0; nn < N; nn++) sum += c[nn];
-                sums[q * B + bb] = sum;
+                const double* c = contrib + q * cslots + bb * cper;
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+                int nn = 0;
+                for (; nn + 5 <= cper; nn += 5) { s0 += c[nn]; s1 += c[nn + 1]; s2 += c[nn + 2]; s3 += c[nn + 3]; s4 += c[nn + 4]; }
+                for (; nn < cper; nn++) s0 += c[nn];
+                sums_w[q * B + bb] = ((s0 + s1) + (s2 + s3)) + s4;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_sums_ready[sbuf]);
             PF_MARK(2);
             if (use_bulk && lane == 0) bulk_store_wait_read();
             __syncwarp();
             PF_MARK(3);
-            stage_env(tile + 2 * G, (it + 2) % 3);
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bar_env[(it + 2) % 3]);
-                mbar_arrive(&bar_free[buf]);                  // contribution + obs buffers of this tile are free again
-            }
+            if (lane == 0) mbar_arrive(&bar_free[buf]);       // contribution + obs buffers of this tile are free again
             PF_MARK(4);
+        }
+        PF_FLUSH(0);
+        if (lane == 0) bulk_store_wait_read();
+        return;
+    }
+    if (tid >= kPfCompute) {
+        // =================================================================== epilogue warp 0: env scratch, finalisation
+        const int lane = tid - kPfCompute;
+        int4 envA = make_int4(0, 0, 0, 0), envQ = make_int4(0, 0, 0, 0), r0, r1, r2, r3;
+        r0 = r1 = r2 = r3 = make_int4(0, 0, 0, 0);
+        // two-deep load pipeline, no dependent load is ever waited for in the loop: env4 of a tile is fetched one
+        // iteration before its step_row (whose address needs env4.t)
+        auto load_env4 = [&](int tile) {                      // lane < B: env4 of env tile*B + lane -> envQ
+            const int e = tile * B + lane;
+            if (lane < B && tile < ntiles && e < p.E) envQ = ld_keep_v4(p.env4 + e, keep);
+        };
+        auto load_rows = [&](int tile) {                      // step_row[t] of the env in envA -> r0..r3
+            const int e = tile * B + lane;
+            if (lane < B && tile < ntiles && e < p.E) {
+                const int4* r = reinterpret_cast<const int4*>(p.step_row + min(envA.x, p.T - 2));
+                r0 = ld_keep_v4(r, keep); r1 = ld_keep_v4(r + 1, keep); r2 = ld_keep_v4(r + 2, keep); r3 = ld_keep_v4(r + 3, keep);
+            }
+        };
+        auto stage_env = [&](int tile, int ebuf) -> bool {    // returns: some env of the tile finishes (and resets)
+            const int e = tile * B + lane;
+            int fl = 0;
+            if (lane < B && tile < ntiles && e < p.E) {
+                PfEnv& es = reinterpret_cast<PfEnv*>(envs0 + ebuf * p.pf_envs_b)[lane];
+                es.t = envA.x; es.t_start = envA.y; es.ep_count = envA.z;
+                if (envA.x + 1 == envA.y + p.L) fl |= EF_DONE | EF_RESET;
+                if (((uint32_t)r3.w & TF_TRIGGER) && p.calc_deg) fl |= EF_TRIGGER;
+                if ((uint32_t)r3.w & TF_LUNCH) fl |= EF_LUNCH;
+                es.flags = fl;
+                es.S = __hiloint2double(r0.y, r0.x); es.F_cr = __hiloint2double(r0.w, r0.z);
+                es.F_dr = __hiloint2double(r1.y, r1.x); es.Rfac = __hiloint2double(r1.w, r1.z);
+                es.pv_share = __hiloint2double(r2.y, r2.x); es.gml = __hiloint2double(r2.w, r2.z);
+                es.pvv = __hiloint2double(r3.y, r3.x);
+            }
+            const bool any = __any_sync(0xffffffffu, (fl & EF_RESET) != 0);
+            if (lane == 0) s_any_reset[ebuf] = any;
+            return any;
+        };
+        // env scratch of the first three tiles; the loads of the next two go in flight
+        load_env4(tile0); envA = envQ; load_rows(tile0); stage_env(tile0, 0);
+        __syncwarp(); if (lane == 0) mbar_arrive(&bar_env[0]);
+        load_env4(tile0 + G); envA = envQ; load_rows(tile0 + G); stage_env(tile0 + G, 1);
+        __syncwarp(); if (lane == 0) mbar_arrive(&bar_env[1]);
+        load_env4(tile0 + 2 * G); envA = envQ; load_rows(tile0 + 2 * G); stage_env(tile0 + 2 * G, 2);
+        __syncwarp(); if (lane == 0) mbar_arrive(&bar_env[2]);
+        load_env4(tile0 + 3 * G); envA = envQ; load_rows(tile0 + 3 * G);
+        load_env4(tile0 + 4 * G);
+
+        int it = 0;
+        for (int tile = tile0; tile < ntiles; tile += G, it++) {
+            const int sbuf = it & 1;
+            const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % kPfEnvs) * p.pf_envs_b);
+            const double* sums_r = sums + sbuf * sums_stride;
+            const int e0 = tile * B;
+            const int nb = min(B, p.E - e0);
+
+            // env scratch three tiles ahead goes first: its buffer has been free since the previous iteration (tile-1
+            // is complete on the compute side, waited for through warp 1's sums, and finalised here)
+            stage_env(tile + 3 * G, (it + 3) % kPfEnvs);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_env[(it + 3) % kPfEnvs]);
+            envA = envQ; load_rows(tile + 4 * G);             // in flight during this iteration
+            load_env4(tile + 5 * G);
+            double ep_prev = 0;                               // episode return so far (lane < nb), fetched ahead of its use
+            if (lane < nb) ep_prev = p.env_f64[(size_t)EF_EP_RETURN * p.E + e0 + lane];
+            mbar_wait(&bar_sums_ready[sbuf], (uint32_t)((it >> 1) & 1));   // warp 1 has summed tile `tile`
 
             // ---- env-level finalisation: one lane per env
             for (int bb = lane; bb < nb; bb += 32) {
                 const int e = e0 + bb;
                 const PfEnv& es = envs[bb];
                 double* stt = p.stats + (size_t)(tile % kStatStripes) * FLEET_S__COUNT;
-                const double cashflow = sums[Q_CASH * B + bb];
-                double reward = sums[Q_REWARD * B + bb];
-                const double margin = es.gml - sums[Q_ATH * B + bb] * p.evse + es.pvv;             // load_calculation.py:93
+                const double cashflow = sums_r[Q_CASH * B + bb];
+                double reward = sums_r[Q_REWARD * B + bb];
+                const double margin = es.gml - sums_r[Q_ATH * B + bb] * p.evse + es.pvv;             // load_calculation.py:93
                 const double overload = fabs(margin < 0.0 ? margin : 0.0);
                 if (overload > 0) {
                     const double rel = overload / p.grid + 1;                                      // fleet_environment.py:496
@@ -1014,8 +1098,8 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
                     reward += pen * p.pen_ovl;                                                     // score_config.py:33-41
                     atomicAdd(stt + FLEET_S_OVERLOAD_KW, overload);
                 }
-                const double soc_viol = fabs(sums[Q_MISS * B + bb]);
-                const double n_viol = sums[Q_NVIOL * B + bb];
+                const double soc_viol = fabs(sums_r[Q_MISS * B + bb]);
+                const double n_viol = sums_r[Q_NVIOL * B + bb];
                 const int dn = (es.flags & EF_DONE) ? 1 : 0;
                 const double ep_ret = ((bb == lane) ? ep_prev : p.env_f64[(size_t)EF_EP_RETURN * p.E + e]) + reward;
                 atomicAdd(stt + FLEET_S_STEPS, 1.0);
@@ -1040,29 +1124,25 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
                 if (p.reward) p.reward[e] = (float)reward;
                 if (p.done) p.done[e] = (uint8_t)dn;
             }
-            __syncwarp();   // sums[] is reused by the next tile
-            PF_MARK(5);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_sums_free[sbuf]);
         }
-        PF_FLUSH(0);
-        if (lane == 0) bulk_store_wait_read();
         return;
     }
 
     // ======================================================================= compute warps
-    const bool have_flips = (*p.n_flips != 0);
     const int j = tid;
     const int b = (N == 1) ? j : (int)__umulhi((unsigned)j, p.n_magic);     // slot -> (env of tile, EV): same for every tile
     const int n = j - b * N;
     const bool slot = j < cstride;
     const int hpos = n < p.Ha ? 2 * N + n : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (n - p.Ha);
 
-    // pipeline registers: only what the arithmetic needs up front is prefetched one tile ahead; the second half of the
-    // schedule record (auxiliary observation terms) and the header element are loaded at the start of the tile and
-    // consumed at its end, which keeps the register footprint below the 3-CTA budget without spills
-    struct In { float a32, hl; double soc, soh, sdeg; int4 r0; int k; };
-    In cur, nxt;
-    cur.a32 = cur.hl = 0.f; cur.soc = cur.sdeg = 0; cur.soh = 1; cur.r0 = make_int4(0, 0, 0, 0); cur.k = 0;
-    nxt = cur;
+    // Input pipeline: the per-slot inputs of a tile (action, soc, hours_left, soh, previous history row, both halves of
+    // ev_rec[t+1], the header element) are copied by the slot's OWN thread into a shared-memory stage with cp.async
+    // (LDGSTS) two tiles ahead.  The bytes in flight live in shared memory instead of registers: ~32 KB per CTA, which
+    // is what the HBM latency x bandwidth product asks for (a register pipeline one tile deep was latency bound), and
+    // since every thread reads back only what it copied itself no barrier is involved, just cp.async.wait_group.
+    const uint32_t stage0 = smem_u32(smem_raw + p.pf_off_stage);
     auto load_env2 = [&](int tile) -> int2 {
         const int e = tile * B + b;
         int2 v = make_int2(0, 0);
@@ -1071,69 +1151,82 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
         }
         return v;
     };
-    auto issue_loads = [&](int tile, const int2 ev, In& in) {
+    auto issue_copies = [&](int tile, const int2 ev, int stage) {
         const int e = tile * B + b;
-        in.k = ev.x - ev.y;
         if (slot && tile < ntiles && e < p.E) {
             const size_t i = (size_t)tile * cstride + j;
-            in.a32 = __ldcs(p.actions + i);
-            in.soc = __ldcs(p.soc + i);
-            in.hl = __ldcs(p.hl + i);
-            in.soh = __ldcs(p.soh + i);
-            in.sdeg = __ldcs(p.hist + (size_t)e * p.RN + (unsigned)((p.calc_deg ? in.k : (in.k & 1)) * N + n));
-            in.r0 = ld_keep_v4(p.ev_rec + (size_t)min(ev.x + 1, p.T - 1) * N + n, keep);
+            const uint32_t st = stage0 + (uint32_t)stage * kPfStageBytes;
+            const uint64_t stream = l2_evict_first_policy(), keep = l2_evict_last_policy();   // made here: not held in registers
+            const int k = ev.x - ev.y;
+            const int t1 = min(ev.x + 1, p.T - 1);
+            const int4* rp = reinterpret_cast<const int4*>(p.ev_rec + (size_t)t1 * N + n);
+            cp_async4_hint(st + kPfStA32 + j * 4, p.actions + i, stream);
+            cp_async8_hint(st + kPfStSoc + j * 8, p.soc + i, stream);
+            cp_async4_hint(st + kPfStHl + j * 4, p.hl + i, stream);
+            cp_async8_hint(st + kPfStSoh + j * 8, p.soh + i, stream);
+            cp_async8_hint(st + kPfStSdeg + j * 8, p.hist + (size_t)e * p.RN + (unsigned)((p.calc_deg ? k : (k & 1)) * N + n), stream);
+            cp_async16_hint(st + kPfStR0 + j * 16, rp, keep);
+            cp_async16_hint(st + kPfStR1 + j * 16, rp + 1, keep);
+            if (n < H) cp_async4_hint(st + kPfStHv + j * 4, p.hdr + (size_t)t1 * p.hdr_stride + n, keep);
         }
+        cp_async_commit();
     };
-    int2 ev1;
     {
         const int2 ev0 = load_env2(tile0);
-        ev1 = load_env2(tile0 + G);
-        issue_loads(tile0, ev0, cur);
+        const int2 ev1 = load_env2(tile0 + G);
+        issue_copies(tile0, ev0, 0);
+        issue_copies(tile0 + G, ev1, 1);
     }
 
     int it = 0;
     PF_DECL();
     PF_START();
     for (int tile = tile0; tile < ntiles; tile += G, it++) {
-        const int buf = it & 1;
-        const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % 3) * envs_b);
-        double* contrib = reinterpret_cast<double*>(contrib0 + buf * contrib_b);
-        float* obs_tile = reinterpret_cast<float*>(obs0 + buf * obs_b);
+        const int buf = it % kPfOut, stg = it & 1;
+        const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % kPfEnvs) * p.pf_envs_b);
+        double* contrib = reinterpret_cast<double*>(contrib0 + buf * p.pf_contrib_b);
+        float* obs_tile = reinterpret_cast<float*>(obs0 + buf * p.pf_obs_b);
         const int e0 = tile * B;
         const int nb = min(B, p.E - e0);
         const bool active = slot && b < nb;
 
-        // ---- loads of the next tile go in flight; env4 two tiles ahead
-        issue_loads(tile + G, ev1, nxt);
-        const int2 ev2 = load_env2(tile + 2 * G);
+        // ---- this tile's inputs: wait for the thread's own copies; they are read from the stage where they are needed
+        // and the stage is refilled (for the tile after next) at the end of the tile, one tile period ahead of its use
+        const int2 ev_next = load_env2(tile + 2 * G);
+        cp_async_wait_group<1>();
+        const unsigned char* stp = smem_raw + p.pf_off_stage + stg * kPfStageBytes;
         PF_MARK(4);
-        mbar_wait(&bar_env[it % 3], (uint32_t)((it / 3) & 1));       // env scratch of this tile is staged
+        mbar_wait(&bar_env[it % kPfEnvs], (uint32_t)((it / kPfEnvs) & 1));   // env scratch of this tile is staged
         PF_SETTLE();
         PF_MARK(0);
-        if (it >= 2) mbar_wait(&bar_free[buf], (uint32_t)(((it >> 1) - 1) & 1));   // contribution + obs buffers are free again
+        if (it >= kPfOut) mbar_wait(&bar_free[buf], (uint32_t)(((it / kPfOut) - 1) & 1));   // contribution + obs buffers are free again
         PF_SETTLE();
         PF_MARK(2);
 
+        double q_rew = 0, q_cash = 0, q_ath = 0, q_miss = 0, q_nviol = 0;   // this vehicle's terms of the per-env sums
+        double o_soc = 0, o_sdeg = 0;                                       // new state, stored after the hand-off
+        float o_hl = 0.f;
+        size_t o_hist = 0;
         if (active) {
             const PfEnv& es = envs[b];
             float* orow = obs_tile + b * D;
             const size_t i = (size_t)tile * cstride + j;
-            // issued now, consumed by the observation stores at the end of the tile
             const int t1 = min(es.t + 1, p.T - 1);
-            const int4 r1 = ld_keep_v4(reinterpret_cast<const int4*>(p.ev_rec + (size_t)t1 * N + n) + 1, keep);
-            float hv = 0.f;
-            if (n < H) hv = ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + n, keep);
+            const int k = es.t - es.t_start;
             EvRec rec;
-            rec.sr = __hiloint2double(cur.r0.y, cur.r0.x); rec.tl = __int_as_float(cur.r0.z);
-            rec.there = (uint8_t)(cur.r0.w & 0xff); rec.there_prev = (uint8_t)((cur.r0.w >> 8) & 0xff); rec.pad = 0;
-            double soc = cur.soc, sdeg = cur.sdeg;
-            float hl = cur.hl;
-            const double soh = cur.soh;
-            const bool flip = have_flips && p.tflip[i] != 0;
+            {
+                const int4 in_r0 = reinterpret_cast<const int4*>(stp + kPfStR0)[j];
+                rec.sr = __hiloint2double(in_r0.y, in_r0.x); rec.tl = __int_as_float(in_r0.z);
+                rec.there = (uint8_t)(in_r0.w & 0xff); rec.there_prev = (uint8_t)((in_r0.w >> 8) & 0xff); rec.pad = 0;
+            }
+            double soc = reinterpret_cast<const double*>(stp + kPfStSoc)[j], sdeg = reinterpret_cast<const double*>(stp + kPfStSdeg)[j];
+            float hl = reinterpret_cast<const float*>(stp + kPfStHl)[j];
+            const double soh = reinterpret_cast<const double*>(stp + kPfStSoh)[j];
+            const bool flip = s_have_flips && p.tflip[i] != 0;
             const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
             const double cap = soh * p.cap0;                                // episode.battery_cap[car]
             const int there = rec.there_prev;                               // db.There at t
-            const double a = (double)cur.a32;
+            const double a = (double)reinterpret_cast<const float*>(stp + kPfStA32)[j];
             double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
             double num = 0;
             if (a >= 0) {                                                   // ev_charger.py:98-156
@@ -1190,28 +1283,51 @@ __global__ void __launch_bounds__(kPfThreads, 3) fleet_step_pf_kernel(const Step
             }
             if (hl != 0.f) sdeg = soc;                                      // :621-623
 
-            __stcs(p.soc + i, soc);
-            __stcs(p.hl + i, hl);
-            __stcs(p.hist + (size_t)(e0 + b) * p.RN + (unsigned)((p.calc_deg ? cur.k + 1 : ((cur.k + 1) & 1)) * N + n), sdeg);
-            contrib[Q_REWARD * cstride + j] = c_cr + c_dr + c_inv + c_oc + c_dep;
-            contrib[Q_CASH * cstride + j] = -1 * c_cost + c_rev;
-            contrib[Q_ATH * cstride + j] = c_ath;
-            contrib[Q_MISS * cstride + j] = c_miss;
-            contrib[Q_NVIOL * cstride + j] = c_nviol;
-            rec.tt = __int_as_float(r1.x); rec.cl = __int_as_float(r1.y);
-            rec.hn = __int_as_float(r1.z); rec.lax = __int_as_float(r1.w);
+            o_soc = soc; o_hl = hl; o_sdeg = sdeg;
+            o_hist = (size_t)(e0 + b) * p.RN + (unsigned)((p.calc_deg ? k + 1 : ((k + 1) & 1)) * N + n);
+            q_rew = c_cr + c_dr + c_inv + c_oc + c_dep;
+            q_cash = -1 * c_cost + c_rev;
+            q_ath = c_ath; q_miss = c_miss; q_nviol = c_nviol;
+            {
+                const int4 r1 = reinterpret_cast<const int4*>(stp + kPfStR1)[j];
+                rec.tt = __int_as_float(r1.x); rec.cl = __int_as_float(r1.y);
+                rec.hn = __int_as_float(r1.z); rec.lax = __int_as_float(r1.w);
+            }
             write_ev_obs<kNorm, kAux>(p, orow, n, soc, hl, rec, flip);
             // time-only part of the observation: element n of this env's header row (+ the rest when N < H)
-            if (n < H) orow[hpos] = hv;
+            if (n < H) orow[hpos] = reinterpret_cast<const float*>(stp + kPfStHv)[j];
             for (int q = n + N; q < H; q += N)
                 orow[q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha)] =
                     ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + q, keep);
         }
+        // contributions: with an even N the two vehicles of a lane pair (same env) are added here, even lane + odd lane
+        if (pair) {
+            q_rew += __shfl_xor_sync(0xffffffffu, q_rew, 1);
+            q_cash += __shfl_xor_sync(0xffffffffu, q_cash, 1);
+            q_ath += __shfl_xor_sync(0xffffffffu, q_ath, 1);
+            q_miss += __shfl_xor_sync(0xffffffffu, q_miss, 1);
+            q_nviol += __shfl_xor_sync(0xffffffffu, q_nviol, 1);
+        }
+        if (active && !(pair && (j & 1))) {
+            const int cj = pair ? (j >> 1) : j;
+            contrib[Q_REWARD * cslots + cj] = q_rew;
+            contrib[Q_CASH * cslots + cj] = q_cash;
+            contrib[Q_ATH * cslots + cj] = q_ath;
+            contrib[Q_MISS * cslots + cj] = q_miss;
+            contrib[Q_NVIOL * cslots + cj] = q_nviol;
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (bulk store)
         mbar_arrive(&bar_done[buf]);
+        // the new state goes to HBM after the hand-off: the fence above (MEMBAR + proxy fence) then only has shared-memory
+        // stores to wait for, not these
+        if (active) {
+            const size_t i = (size_t)tile * cstride + j;
+            __stcs(p.soc + i, o_soc);
+            __stcs(p.hl + i, o_hl);
+            __stcs(p.hist + o_hist, o_sdeg);
+        }
+        issue_copies(tile + 2 * G, ev_next, stg);             // refill the stage this tile has just consumed
         PF_MARK(3);
-        cur = nxt;
-        ev1 = ev2;
     }
     PF_FLUSH(8);
 }
@@ -1638,7 +1754,7 @@ __device__ __forceinline__ void post_finish_lists(const StepParams& p) {
 template <bool kNorm, bool kAux>
 __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = p.N, D = p.D;
+    const int N = p.N;
     double* vring = reinterpret_cast<double*>(smem_raw);
     const int cap = p.L + 2;
     uint32_t* recs = reinterpret_cast<uint32_t*>(vring + kStackS * kPostThreads);
@@ -2494,6 +2610,17 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_pf(h), kPfThreads, smpf) == cudaSuccess && per_sm >= 1) {
                 h->smem_pf = smpf;
                 const int ntiles = (E + p.B - 1) / p.B;
+                p.pf_ntiles = ntiles;
+                p.pf_pair = (N & 1) ? 0 : 1;
+                p.pf_cslots = pf_contrib_slots(p.B, N);
+                p.pf_cper = p.pf_pair ? N / 2 : N;
+                p.pf_envs_b = (int)align16((size_t)p.B * sizeof(PfEnv));
+                p.pf_contrib_b = (int)align16((size_t)kNQ * p.pf_cslots * 8);
+                p.pf_obs_b = (int)align16((size_t)p.B * h->D * 4);
+                p.pf_off_contrib = kPfEnvs * p.pf_envs_b;
+                p.pf_off_sums = p.pf_off_contrib + kPfOut * p.pf_contrib_b;
+                p.pf_off_obs = p.pf_off_sums + 2 * (int)align16((size_t)kNQ * p.B * 8);
+                p.pf_off_stage = (int)align16((size_t)p.pf_off_obs + (size_t)kPfOut * p.pf_obs_b);
                 const int g = prop.multiProcessorCount * per_sm;
                 h->grid_pf = g < ntiles ? g : ntiles;
                 h->use_pf = 1;

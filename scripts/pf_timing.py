@@ -34,3 +34,4 @@ print("epilogue warp, cycles per tile: pre-Done %.0f | wait Done %.0f | store+su
       % (*ep, ep.sum()))
 cw = v[[8, 10, 11, 12]] / (K * ntiles * 8)
 print("compute warps, cycles per tile: wait Env %.0f | wait Free %.0f | compute %.0f | issue next loads %.0f | total %.0f" % (*cw, cw.sum()))
+print("epilogue warps by (%warpid & 3), summed over the launches:", v[12:16] / K)
