@@ -21,7 +21,7 @@ EXPORTS = [
     "fleet_abi_version", "fleet_create", "fleet_destroy", "fleet_obs_dim", "fleet_num_evs", "fleet_num_envs",
     "fleet_reset", "fleet_step", "fleet_step_host", "fleet_set_next_start", "fleet_get_state", "fleet_set_state",
     "fleet_field_info", "fleet_get_stats", "fleet_reset_stats", "fleet_check_errors", "fleet_launch_count",
-    "fleet_device_bytes", "fleet_last_error",
+    "fleet_device_bytes", "fleet_last_error", "fleet_set_timing", "fleet_get_timing", "fleet_step_kernel_name",
 ]
 
 
@@ -59,6 +59,10 @@ def load_library(path: str = LIB_PATH):
     L.fleet_launch_count.restype = i64
     L.fleet_device_bytes.argtypes = [vp]
     L.fleet_device_bytes.restype = i64
+    L.fleet_step_kernel_name.argtypes = [vp]
+    L.fleet_step_kernel_name.restype = C.c_char_p
+    L.fleet_set_timing.argtypes = [vp, i32]
+    L.fleet_get_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]
     L.fleet_last_error.argtypes = [vp]
     L.fleet_last_error.restype = C.c_char_p
     if L.fleet_abi_version() != ABI_VERSION:
@@ -194,6 +198,20 @@ class FleetStepHandle:
         flags = C.c_uint32(0)
         self._check(self.lib.fleet_check_errors(self._h, C.byref(flags), _stream_ptr(self.device)), "fleet_check_errors")
         return int(flags.value)
+
+    def set_timing(self, enable=True):
+        self._check(self.lib.fleet_set_timing(self._h, 1 if enable else 0), "fleet_set_timing")
+
+    def get_timing(self):
+        """(step-kernel ms, post-kernel ms, steps) summed over the steps since set_timing (at most the last 1024)."""
+        a, b, n = C.c_double(0), C.c_double(0), C.c_int64(0)
+        self._check(self.lib.fleet_get_timing(self._h, C.byref(a), C.byref(b), C.byref(n)), "fleet_get_timing")
+        return a.value, b.value, int(n.value)
+
+    @property
+    def step_kernel_name(self):
+        """Name of the step kernel fleet_create selected for this handle."""
+        return self.lib.fleet_step_kernel_name(self._h).decode()
 
     @property
     def launch_count(self):

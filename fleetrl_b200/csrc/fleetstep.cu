@@ -982,6 +982,14 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             if (use_bulk) {
                 // the writers have run fence.proxy.async before arriving on bar_done: no second fence here
                 if (lane == 0) bulk_store_s2g_nofence(p.obs + (size_t)e0 * D, obs_tile, (uint32_t)(B * D * 4));
+            } else if (p.bulk_ok && (D & 3) == 0) {
+                // rows of finishing envs go to terminal_obs: one bulk store per env row (D*4 bytes, 16-byte aligned)
+                if (lane < nb) {
+                    const int e = e0 + lane;
+                    float* dst = (envs[lane].flags & EF_RESET) ? (p.terminal_obs ? p.terminal_obs + (size_t)e * D : nullptr)
+                                                               : (p.obs ? p.obs + (size_t)e * D : nullptr);
+                    if (dst) bulk_store_s2g_nofence(dst, obs_tile + (size_t)lane * D, (uint32_t)(D * 4));
+                }
             } else {
                 for (int w = lane; w < nb * D; w += 32) {
                     const int bb = w / D;
@@ -1007,14 +1015,14 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_sums_ready[sbuf]);
             PF_MARK(2);
-            if (use_bulk && lane == 0) bulk_store_wait_read();
+            if (p.bulk_ok && (use_bulk ? lane == 0 : (lane < nb && (D & 3) == 0))) bulk_store_wait_read();
             __syncwarp();
             PF_MARK(3);
             if (lane == 0) mbar_arrive(&bar_free[buf]);       // contribution + obs buffers of this tile are free again
             PF_MARK(4);
         }
         PF_FLUSH(0);
-        if (lane == 0) bulk_store_wait_read();
+        bulk_store_wait_read();
         return;
     }
     if (tid >= kPfCompute) {
@@ -1832,6 +1840,9 @@ __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepPara
 //      last bits only, inside the stated SOH tolerance).
 //   D. per-vehicle fade update, then the env's reset if it also finished.
 // Reset-only entries are taken by quarter CTAs (64 threads) afterwards.
+#ifndef KPOST2_BWARPS
+#define KPOST2_BWARPS 8
+#endif
 constexpr int kPost2Threads = 256;
 
 struct Post2Misc {   // per-chunk scalars in shared memory
@@ -1851,6 +1862,8 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
     int* s_rfl = s_m + NC;                                                 // [NC] rainflow_length of the vehicle
     double* s_msum = reinterpret_cast<double*>(s_rfl + NC);                // [NC] sum of cycle means (2*NC ints before it)
     __shared__ int s_w;
+    __shared__ int2 s_ent;
+    __shared__ int4 s_ev;
     __shared__ double s_deg;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int count_d = p.wl_count[0], count_r = p.wl_count[1];
@@ -1858,15 +1871,27 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
                  temp_ref = 25, k_dt = 4.14E-10, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
     PT_START();
 
+    // The first entry of a CTA is static (entry blockIdx.x), further ones come from a counter; thread 0 fetches the NEXT
+    // entry's list record and env4 while the current one is processed, so the two dependent round trips are hidden.
+    if (tid == 0) {
+        s_w = blockIdx.x; s_deg = 0;
+        if (s_w < count_d) { s_ent = p.wl[s_w]; s_ev = p.env4[s_ent.x]; }
+    }
     for (;;) {
-        if (tid == 0) { s_w = atomicAdd(p.wl_count + 2, 1); s_deg = 0; }
         __syncthreads();
         const int w = s_w;
         if (w >= count_d) break;
-        const int2 ent = p.wl[w];
+        const int2 ent = s_ent;
         const int e = ent.x, wf = ent.y;
-        const int4 ev = p.env4[e];                      // {t (already advanced), t_start, ep_count}
+        const int4 ev = s_ev;                           // {t (already advanced), t_start, ep_count}
         const int len = ev.x - ev.y + 1;                // history rows 0..k+1 where k+1 = t - t_start
+        int w_next = 0;
+        int2 ent_next = make_int2(0, 0);
+        int4 ev_next = make_int4(0, 0, 0, 0);
+        if (tid == 0) {
+            w_next = atomicAdd(p.wl_count + 2, 1) + (int)gridDim.x;
+            if (w_next < count_d) { ent_next = p.wl[w_next]; ev_next = p.env4[ent_next.x]; }
+        }
         const double* hbase = p.hist + (size_t)e * p.R * N;
 
         if (p.deg_mode == FLEET_DEG_EMPIRICAL) {
@@ -1917,6 +1942,7 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
                             const double d = xb - xa;
                             const bool nz = valid && (xb != xa);
                             const unsigned nzmask = __ballot_sync(0xffffffffu, nz);
+                            if (nzmask == 0) continue;               // 32 equal samples (vehicle away / idle): nothing happens
                             const unsigned lower = nzmask & ((1u << lane) - 1u);
                             const int src = lower ? 31 - __clz(lower) : 0;
                             const double d_lo = __shfl_sync(0xffffffffu, d, src);
@@ -1936,21 +1962,29 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
                     }
                     if (lane == j) my_nr = nr;
                 }
+#if KPOST2_BWARPS == 8
                 __syncwarp();
                 PT_MARK(1);
                 if (lane < cpw && warp * cpw + lane < nc) {
                     const int c = warp * cpw + lane;
+#else
+                // phase B on fewer warps (more lanes each): fewer warps compete for issue slots with serial code
+                if (lane < cpw && warp * cpw + lane < nc) s_m[warp * cpw + lane] = my_nr;
+                __syncthreads();
+                PT_MARK(1);
+                const int cpb = (nc + KPOST2_BWARPS - 1) / KPOST2_BWARPS;
+                if (warp < KPOST2_BWARPS && lane < cpb && warp * cpb + lane < nc) {
+                    const int c = warp * cpb + lane;
+                    my_nr = s_m[c];
+#endif
                     const double* col = rv + c * LP;
                     uint16_t* st = stk + c * LP;
                     uint32_t* rc = recs + c * LP;
                     const int nr = (len >= 2) ? my_nr : 0;
                     int lo = 0, hi = 0, m = 0;
                     double mean_sum = 0;
-                    // the top five stack entries are mirrored in registers (a4/o4 = top; a_k valid iff depth >= 5-k):
-                    // after a cycle closes, the next three-point test runs on registers while the two entries that move
-                    // into the mirror are fetched from shared memory off the critical path
-                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-                    int o0 = 0, o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+                    double v1 = 0, v2 = 0, v3 = 0;                   // values of the top three stack entries (v3 = top)
+                    int o1 = 0, o2 = 0, o3 = 0;                      // their ordinals in the reversal list
 #define RF2_EMIT(oa, xa, ob, xb_, full)                                                       \
     do {                                                                                      \
         mean_sum += 0.5 * ((xa) + (xb_));                                                     \
@@ -1967,18 +2001,17 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
                                 const int r = r0 + u;
                                 if (r < nr) {
                                     st[hi] = (uint16_t)r; hi++;
-                                    a0 = a1; o0 = o1; a1 = a2; o1 = o2; a2 = a3; o2 = o3; a3 = a4; o3 = o4; a4 = vb[u]; o4 = r;
+                                    v1 = v2; o1 = o2; v2 = v3; o2 = o3; v3 = vb[u]; o3 = r;
                                     while (hi - lo >= 3) {
-                                        const double X = fabs(a4 - a3), Y = fabs(a3 - a2);
+                                        const double X = fabs(v3 - v2), Y = fabs(v2 - v1);
                                         if (X < Y) break;
-                                        if (hi - lo == 3) { RF2_EMIT(o2, a2, o3, a3, 0); lo++; }
+                                        if (hi - lo == 3) { RF2_EMIT(o1, v1, o2, v2, 0); lo++; }
                                         else {
-                                            RF2_EMIT(o2, a2, o3, a3, 1);
+                                            RF2_EMIT(o1, v1, o2, v2, 1);
                                             hi -= 2;
-                                            st[hi - 1] = (uint16_t)o4;
-                                            a3 = a1; o3 = o1; a2 = a0; o2 = o0;
-                                            if (hi - lo >= 4) { o1 = st[hi - 4]; a1 = col[o1]; }
-                                            if (hi - lo >= 5) { o0 = st[hi - 5]; a0 = col[o0]; }
+                                            st[hi - 1] = (uint16_t)o3;
+                                            o2 = st[hi - 2]; v2 = col[o2];
+                                            if (hi - lo >= 3) { o1 = st[hi - 3]; v1 = col[o1]; }
                                         }
                                     }
                                 }
@@ -2077,7 +2110,8 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
         if (tid == 0 && s_deg != 0)
             atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
         if (wf & WL_RESET) post_reset_env<kNorm, kAux>(p, e, ev, tid, kPost2Threads);
-        __syncthreads();                                             // s_w / s_deg are rewritten by thread 0
+        __syncthreads();                                             // everybody has read s_w / s_ent / s_ev / s_deg
+        if (tid == 0) { s_w = w_next; s_ent = ent_next; s_ev = ev_next; s_deg = 0; }
         PT_MARK(5);
     }
 
@@ -2186,6 +2220,8 @@ __global__ void reduce_stats_kernel(const double* stats, double* dst, double pri
 
 // =============================================================================================== host side / C ABI
 
+constexpr int kTimingRing = 1024;   // fleet_set_timing keeps the event triplets of the last kTimingRing steps
+
 struct FleetHandle {
     FleetConsts c;
     int device = 0;
@@ -2201,6 +2237,10 @@ struct FleetHandle {
     int use_post2 = 0, grid_post2 = 0;
     size_t smem_post2 = 0;
     int max_smem_optin = 0;
+    // optional per-kernel timing (fleet_set_timing): event triplets {before step, between, after post} in a ring
+    int timing = 0;
+    std::vector<cudaEvent_t> tev;
+    int64_t tcount = 0;
     // host-call staging (fleet_step_host)
     float* h_actions_dev = nullptr; float* h_obs_dev = nullptr; float* h_reward_dev = nullptr; uint8_t* h_done_dev = nullptr;
 };
@@ -2302,6 +2342,42 @@ int fleet_obs_dim(const FleetHandle* h) { return h ? h->D : FLEET_E_INVALID; }
 int fleet_num_evs(const FleetHandle* h) { return h ? h->N : FLEET_E_INVALID; }
 int fleet_num_envs(const FleetHandle* h) { return h ? h->E : FLEET_E_INVALID; }
 int64_t fleet_launch_count(const FleetHandle* h) { return h ? h->launches : 0; }
+
+const char* fleet_step_kernel_name(const FleetHandle* h) {
+    if (!h) return "";
+    return h->use_tma ? "fleet_step_tma_kernel" : (h->use_pf ? "fleet_step_pf_kernel" : "fleet_step_kernel");
+}
+
+int fleet_set_timing(FleetHandle* h, int32_t enable) {
+    if (!h) return FLEET_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (enable && h->tev.empty()) {
+        h->tev.resize((size_t)kTimingRing * 3);
+        for (auto& ev : h->tev) CUDA_TRY(h, cudaEventCreate(&ev));
+    }
+    h->timing = enable ? 1 : 0;
+    h->tcount = 0;
+    return FLEET_OK;
+}
+
+int fleet_get_timing(FleetHandle* h, double* step_ms, double* post_ms, int64_t* steps) {
+    if (!h) return FLEET_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int64_t n = h->tcount < kTimingRing ? h->tcount : kTimingRing;
+    double a = 0, b = 0;
+    for (int64_t k = 0; k < n; k++) {
+        cudaEvent_t* tev = &h->tev[(size_t)k * 3];
+        float t0 = 0, t1 = 0;
+        CUDA_TRY(h, cudaEventSynchronize(tev[2]));
+        CUDA_TRY(h, cudaEventElapsedTime(&t0, tev[0], tev[1]));
+        CUDA_TRY(h, cudaEventElapsedTime(&t1, tev[1], tev[2]));
+        a += t0; b += t1;
+    }
+    if (step_ms) *step_ms = a;
+    if (post_ms) *post_ms = b;
+    if (steps) *steps = n;
+    return FLEET_OK;
+}
 #ifdef PF_TIMING
 int32_t fleet_debug_pf_clk(unsigned long long* out, int32_t reset) {
     cudaDeviceSynchronize();
@@ -2323,6 +2399,7 @@ int64_t fleet_device_bytes(const FleetHandle* h) { return h ? h->bytes : 0; }
 int fleet_destroy(FleetHandle* h) {
     if (!h) return FLEET_E_INVALID;
     cudaSetDevice(h->device);
+    for (cudaEvent_t ev : h->tev) cudaEventDestroy(ev);
     for (void* ptr : h->allocs) cudaFree(ptr);
     delete h;
     return FLEET_OK;
@@ -2692,15 +2769,21 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     CUDA_TRY(h, cudaSetDevice(h->device));
     StepParams p = h->p;
     p.actions = actions_dev; p.obs = obs_dev; p.reward = reward_dev; p.done = done_dev; p.terminal_obs = terminal_obs_dev;
+    if ((((uintptr_t)obs_dev) | ((uintptr_t)terminal_obs_dev)) & 15) p.bulk_ok = 0;   // bulk stores need 16-byte aligned rows
+    cudaEvent_t* tev = nullptr;
+    if (h->timing && !h->tev.empty()) tev = &h->tev[(size_t)(h->tcount % kTimingRing) * 3];
+    if (tev) cudaEventRecord(tev[0], (cudaStream_t)stream);
     if (h->use_tma) fleet_launch_tma(h, p, (cudaStream_t)stream);
     else if (h->use_pf) pick_pf(h)<<<h->grid_pf, kPfThreads, h->smem_pf, (cudaStream_t)stream>>>(p);
     else pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
     h->launches++;
+    if (tev) cudaEventRecord(tev[1], (cudaStream_t)stream);
     if (h->need_post) {   // daily degradation, then auto-reset, for the envs the step kernel put on the work list
         if (h->use_post2) pick_post2(h)<<<h->grid_post2, kPost2Threads, h->smem_post2, (cudaStream_t)stream>>>(p);
         else pick_post(h)<<<h->grid_post, kPostThreads, h->smem_post, (cudaStream_t)stream>>>(p);
         h->launches++;
     }
+    if (tev) { cudaEventRecord(tev[2], (cudaStream_t)stream); h->tcount++; }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, FLEET_E_CUDA, std::string("fleet_step launch: ") + cudaGetErrorString(e));
     return FLEET_OK;

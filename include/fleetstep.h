@@ -219,6 +219,13 @@ int fleet_check_errors(FleetHandle* h, uint32_t* flags_host, void* stream);
 /* Number of kernel launches issued through this handle so far (bench.py reports it as gpu_launches). */
 int64_t fleet_launch_count(const FleetHandle* h);
 
+/* Optional per-kernel timing for measurement (bench.py's roofline line): when enabled, fleet_step brackets the step
+ * kernel and the post kernel with CUDA events on the caller's stream; fleet_get_timing synchronises them and returns
+ * the summed durations (ms) over the last <= 1024 steps since fleet_set_timing.  No reference counterpart. */
+const char* fleet_step_kernel_name(const FleetHandle* h);   /* which step kernel fleet_create selected */
+int fleet_set_timing(FleetHandle* h, int32_t enable);
+int fleet_get_timing(FleetHandle* h, double* step_kernel_ms, double* post_kernel_ms, int64_t* steps);
+
 /* Bytes of device memory owned by the handle. */
 int64_t fleet_device_bytes(const FleetHandle* h);
 
