@@ -21,7 +21,7 @@ EXPORTS = [
     "fleet_abi_version", "fleet_create", "fleet_destroy", "fleet_obs_dim", "fleet_num_evs", "fleet_num_envs",
     "fleet_reset", "fleet_step", "fleet_step_host", "fleet_set_next_start", "fleet_get_state", "fleet_set_state",
     "fleet_field_info", "fleet_get_stats", "fleet_reset_stats", "fleet_check_errors", "fleet_launch_count",
-    "fleet_device_bytes", "fleet_last_error", "fleet_set_timing", "fleet_get_timing", "fleet_step_kernel_name",
+    "fleet_device_bytes", "fleet_last_error", "fleet_set_timing", "fleet_get_timing", "fleet_step_kernel_name", "fleet_policy_actions", "fleet_policy_reset",
 ]
 
 
@@ -59,6 +59,8 @@ def load_library(path: str = LIB_PATH):
     L.fleet_launch_count.restype = i64
     L.fleet_device_bytes.argtypes = [vp]
     L.fleet_device_bytes.restype = i64
+    L.fleet_policy_actions.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    L.fleet_policy_reset.argtypes = [vp, vp]
     L.fleet_step_kernel_name.argtypes = [vp]
     L.fleet_step_kernel_name.restype = C.c_char_p
     L.fleet_set_timing.argtypes = [vp, i32]
@@ -198,6 +200,20 @@ class FleetStepHandle:
         flags = C.c_uint32(0)
         self._check(self.lib.fleet_check_errors(self._h, C.byref(flags), _stream_ptr(self.device)), "fleet_check_errors")
         return int(flags.value)
+
+    POLICIES = {"uncontrolled": 0, "distributed": 1, "night": 2}
+
+    def policy_actions(self, policy, out=None, charging_hour=0, charging_minute=0, max_hours=0):
+        """Actions [E, N] float32 of a rule-based baseline policy at every env's current time (benchmarking/*.py)."""
+        if out is None:
+            out = torch.empty((self.E, self.N), dtype=torch.float32, device=self.device)
+        self._chk_tensor(out, (self.E, self.N), torch.float32, "actions")
+        self._check(self.lib.fleet_policy_actions(self._h, self.POLICIES[policy], int(charging_hour), int(charging_minute),
+                                                  int(max_hours), _dptr(out), _stream_ptr(self.device)), "fleet_policy_actions")
+        return out
+
+    def policy_reset(self):
+        self._check(self.lib.fleet_policy_reset(self._h, _stream_ptr(self.device)), "fleet_policy_reset")
 
     def set_timing(self, enable=True):
         self._check(self.lib.fleet_set_timing(self._h, 1 if enable else 0), "fleet_set_timing")

@@ -2172,6 +2172,53 @@ __global__ void init_state_kernel(StepParams p) {
 }
 
 // field gathers that are not plain arrays
+// Rule-based charging policies of the reference's benchmarking scripts, one thread per (env, EV); the actions are what
+// those scripts hand to VecEnv.step, as float32 (the action space's dtype):
+//   uncontrolled  benchmarking/uncontrolled_charging.py:51-54   a = 1
+//   distributed   benchmarking/distributed_charging.py:50-54    a = clip(hours_needed / (hours_left + 0.001), 0, 1) from the
+//                 SCHEDULE observation at the current time (FleetEnv.get_dist_factor, fleet_environment.py:782-799)
+//   night         benchmarking/night_charging.py:81-98          a = 1 inside a charging window that opens at
+//                 (charging_hour, charging_minute) and stays open for more than int(max_time_needed) hours, 0 outside; the
+//                 caretaker use case follows the distributed rule between 11:00 and 14:59.  The window flag and its
+//                 opening time are per-env state (st_in -> st_out), carried across episodes like the script's locals.
+__global__ void policy_kernel(StepParams p, int policy, int ch_hour, int ch_minute, int max_h, const uint16_t* __restrict__ tod,
+                              const int2* __restrict__ st_in, int2* __restrict__ st_out, float* __restrict__ actions) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)p.E * p.N) return;
+    const int e = (int)(i / p.N), n = (int)(i - (size_t)e * p.N);
+    const int t = min(p.env4[e].x, p.T - 1);
+    float a = 1.f;
+    if (policy != FLEET_POLICY_UNCONTROLLED) {
+        const EvRec rec = load_rec(&p.ev_rec[(size_t)t * p.N + n]);
+        const bool flip = (*p.n_flips != 0) && p.tflip[i] != 0;
+        const double tgt = flip ? 0.9 : p.target;
+        const double cl = tgt * (double)rec.there - rec.sr;                       // observer_bl_pv.py:86-88
+        const double hn = cl * p.lc_batt_cap / p.hn_den;                          // :89
+        double d = hn / ((double)rec.tl + 0.001);                                 // fleet_environment.py:799
+        d = d < 0 ? 0 : (d > 1 ? 1 : d);
+        if (policy == FLEET_POLICY_DISTRIBUTED) {
+            a = (float)d;
+        } else {
+            const int hour = tod[t] / 60, minute = tod[t] % 60;
+            int2 st = st_in[e];                                                   // {charging, index of the window start}
+            if (p.is_ct && hour >= 11 && hour <= 14) {
+                a = (float)d;                                                     // night_charging.py:84-87 (state untouched)
+            } else {
+                if ((ch_hour <= hour && ch_minute <= minute) || st.x) {           // :89
+                    if (!st.x) st.y = t;
+                    st.x = 1;
+                    a = 1.f;
+                } else {
+                    a = 0.f;
+                }
+                if (st.x && (double)(t - st.y) * p.dt > (double)max_h) st.x = 0;  // :97-98
+            }
+            if (n == 0) st_out[e] = st;
+        }
+    }
+    actions[i] = a;
+}
+
 __global__ void gather_field_kernel(StepParams p, int field, void* dst) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t EN = (size_t)p.E * p.N;
@@ -2237,6 +2284,10 @@ struct FleetHandle {
     int use_post2 = 0, grid_post2 = 0;
     size_t smem_post2 = 0;
     int max_smem_optin = 0;
+    // rule-based policies (fleet_policy_actions): minute of day per table row; night-charging state, double buffered
+    uint16_t* tod = nullptr;
+    int2* pol_state[2] = {nullptr, nullptr};
+    int pol_flip = 0;
     // optional per-kernel timing (fleet_set_timing): event triplets {before step, between, after post} in a ring
     int timing = 0;
     std::vector<cudaEvent_t> tev;
@@ -2597,6 +2648,12 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     p.max_tl = c.max_time_left; p.max_soc = c.target_soc;                                // oracle_normalization.py:34,49
     p.max_hn = (c.target_soc * c.init_battery_cap) / (c.evse_max_power * c.charging_eff);   // :50-51
     p.ev_rec = d_rec; p.step_row = d_rows; p.hdr = d_hdr;
+    {
+        std::vector<uint16_t> tod((size_t)T);
+        for (int tt = 0; tt < T; tt++) tod[tt] = (uint16_t)(tb->hour[tt] * 60 + tb->minute[tt]);
+        if ((rc = dev_alloc(h, &h->tod, (size_t)T, false))) return rc;
+        CUDA_TRY(h, cudaMemcpy(h->tod, tod.data(), tod.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
 
     p.n_magic = (unsigned int)((0x100000000ull + (unsigned long long)N - 1) / (unsigned long long)N);
     {
@@ -2809,6 +2866,36 @@ int fleet_step_host(FleetHandle* h, const float* actions_host, float* obs_host, 
     if (reward_host) CUDA_TRY(h, cudaMemcpyAsync(reward_host, h->h_reward_dev, (size_t)h->E * 4, cudaMemcpyDeviceToHost, s));
     if (done_host) CUDA_TRY(h, cudaMemcpyAsync(done_host, h->h_done_dev, (size_t)h->E, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
+    return FLEET_OK;
+}
+
+int fleet_policy_actions(FleetHandle* h, int32_t policy, int32_t charging_hour, int32_t charging_minute,
+                         int32_t max_hours, float* actions_dev, void* stream) {
+    if (!h) return FLEET_E_INVALID;
+    if (!actions_dev) return fail(h, FLEET_E_INVALID, "actions_dev is NULL");
+    if (policy < FLEET_POLICY_UNCONTROLLED || policy > FLEET_POLICY_NIGHT) return fail(h, FLEET_E_INVALID, "unknown policy");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    if (policy == FLEET_POLICY_NIGHT && !h->pol_state[0]) {
+        if ((rc = dev_alloc(h, &h->pol_state[0], (size_t)h->E))) return rc;
+        if ((rc = dev_alloc(h, &h->pol_state[1], (size_t)h->E))) return rc;
+    }
+    const size_t cnt = (size_t)h->E * h->N;
+    policy_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        h->p, policy, charging_hour, charging_minute, max_hours, h->tod, h->pol_state[h->pol_flip], h->pol_state[h->pol_flip ^ 1],
+        actions_dev);
+    if (policy == FLEET_POLICY_NIGHT) h->pol_flip ^= 1;
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, FLEET_E_CUDA, std::string("fleet_policy_actions: ") + cudaGetErrorString(e));
+    return FLEET_OK;
+}
+
+int fleet_policy_reset(FleetHandle* h, void* stream) {
+    if (!h) return FLEET_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (int k = 0; k < 2; k++)
+        if (h->pol_state[k]) CUDA_TRY(h, cudaMemsetAsync(h->pol_state[k], 0, (size_t)h->E * sizeof(int2), (cudaStream_t)stream));
     return FLEET_OK;
 }
 

@@ -82,6 +82,7 @@ class FleetVecEnv:
         dev = self.device
         self._obs = torch.zeros((E, D), dtype=torch.float32, device=dev)
         self._term = torch.zeros((E, D), dtype=torch.float32, device=dev)
+        self._night = None          # night-charging window parameters (fleetrl_b200/policies.py), derived on first use
         self._rew = torch.zeros(E, dtype=torch.float32, device=dev)
         self._done = torch.zeros(E, dtype=torch.uint8, device=dev)
         self._actions = None
@@ -155,6 +156,18 @@ class FleetVecEnv:
     @property
     def terminal_observations(self):
         return self._term
+
+    def baseline_actions(self, policy, out=None):
+        """Actions [E, N] (float32, on the device) of one of the reference's rule-based benchmark policies at every env's
+        current time: "uncontrolled" (benchmarking/uncontrolled_charging.py), "distributed" (distributed_charging.py) or
+        "night" (night_charging.py; its window parameters are derived from the schedule once)."""
+        if policy == "night":
+            if self._night is None:
+                from .policies import night_params
+                self._night = night_params(self.built)
+            n = self._night
+            return self.handle.policy_actions("night", out, n.charging_hour, n.charging_minute, n.max_hours)
+        return self.handle.policy_actions(policy, out)
 
     def close(self):
         self.handle.close()

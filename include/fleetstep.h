@@ -222,6 +222,20 @@ int64_t fleet_launch_count(const FleetHandle* h);
 /* Optional per-kernel timing for measurement (bench.py's roofline line): when enabled, fleet_step brackets the step
  * kernel and the post kernel with CUDA events on the caller's stream; fleet_get_timing synchronises them and returns
  * the summed durations (ms) over the last <= 1024 steps since fleet_set_timing.  No reference counterpart. */
+/* Rule-based baseline policies of the reference's benchmarking scripts, evaluated on the device for every env at its
+ * current time: actions_dev float32 [E][N] is what those scripts pass to VecEnv.step (as float32).
+ *   FLEET_POLICY_UNCONTROLLED  a = 1                                       benchmarking/uncontrolled_charging.py:51-54
+ *   FLEET_POLICY_DISTRIBUTED   a = clip(get_dist_factor(), 0, 1)           benchmarking/distributed_charging.py:50-54,
+ *                                                                          fleet_environment.py:782-799
+ *   FLEET_POLICY_NIGHT         charging window opening at (charging_hour, charging_minute), open for more than max_hours
+ *                              hours; caretaker fleets follow the distributed rule from 11:00 to 14:59
+ *                              benchmarking/night_charging.py:81-98 (charging_hour/minute/max_hours as computed at :53-71)
+ * The night policy keeps {window open, opening index} per env inside the handle; fleet_policy_reset clears it. */
+enum { FLEET_POLICY_UNCONTROLLED = 0, FLEET_POLICY_DISTRIBUTED = 1, FLEET_POLICY_NIGHT = 2 };
+int fleet_policy_actions(FleetHandle* h, int32_t policy, int32_t charging_hour, int32_t charging_minute, int32_t max_hours,
+                         float* actions_dev, void* stream);
+int fleet_policy_reset(FleetHandle* h, void* stream);
+
 const char* fleet_step_kernel_name(const FleetHandle* h);   /* which step kernel fleet_create selected */
 int fleet_set_timing(FleetHandle* h, int32_t enable);
 int fleet_get_timing(FleetHandle* h, double* step_kernel_ms, double* post_kernel_ms, int64_t* steps);
