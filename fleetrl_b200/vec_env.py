@@ -82,6 +82,7 @@ class FleetVecEnv:
         dev = self.device
         self._obs = torch.zeros((E, D), dtype=torch.float32, device=dev)
         self._term = torch.zeros((E, D), dtype=torch.float32, device=dev)
+        self._log_idx, self._log_rows = [], {}
         self._night = None          # night-charging window parameters (fleetrl_b200/policies.py), derived on first use
         self._rew = torch.zeros(E, dtype=torch.float32, device=dev)
         self._done = torch.zeros(E, dtype=torch.uint8, device=dev)
@@ -128,6 +129,8 @@ class FleetVecEnv:
             self.handle.step(a, self._obs, self._rew, self._done, self._term)
             obs, rew, done = self._obs, self._rew, self._done.bool()
             done_idx = None
+        if self._log_idx:
+            self._log_step_rows(self._actions)
         return obs, rew, done, self._infos(done_idx)
 
     def step(self, actions):
@@ -156,6 +159,60 @@ class FleetVecEnv:
     @property
     def terminal_observations(self):
         return self._term
+
+    # ---- evaluation log (DataLogger.log_data, utils/data_logger/data_logger.py:21-68) for selected envs
+    LOG_COLUMNS = ("Episode", "Time", "Observation", "Action", "Reward", "Cashflow", "Penalties", "Grid overloading",
+                   "SOC violation", "Degradation", "Charging energy", "SOH")
+
+    def enable_log(self, indices=(0,)):
+        """Record the reference's per-step log rows for the given envs (evaluation runs: a handful of envs; every
+        logged step reads state back from the device).  Rows follow fleet_environment.py:420-432 (reset row) and
+        :679-690 (one row per step that does not end the episode).  "Charging energy" (EvCharger's charge_log) is not
+        kept by the kernels and is logged as NaN."""
+        self._log_idx = [int(i) for i in self._indices(indices)]
+        self._log_rows = {i: [] for i in self._log_idx}
+        self._log_reset_rows(self._log_idx)
+
+    def _log_reset_rows(self, idx):
+        if not idx:
+            return
+        t = self.handle.get("time_idx").cpu().numpy()
+        soh = self.handle.get("soh").cpu().numpy()
+        obs = self._obs.cpu().numpy()
+        N = self.num_cars
+        for i in idx:
+            rows = self._log_rows[i]
+            rows.append({"Episode": len(rows) // int(self.built.consts.episode_steps) + 1,
+                         "Time": pd.Timestamp(self.built.dates[int(t[i])]), "Observation": obs[i].copy(),
+                         "Action": np.zeros(N), "Reward": 0.0, "Cashflow": 0.0, "Penalties": 0.0, "Grid overloading": 0.0,
+                         "SOC violation": 0.0, "Degradation": 0.0, "Charging energy": np.zeros(N), "SOH": soh[i].copy()})
+
+    def _log_step_rows(self, actions):
+        idx = self._log_idx
+        h = self.handle
+        t = h.get("time_idx").cpu().numpy()
+        done = self._done.cpu().numpy().astype(bool)
+        rew, cash = h.get("reward64").cpu().numpy(), h.get("cashflow").cpu().numpy()
+        ovl, viol = h.get("overload").cpu().numpy(), h.get("soc_viol").cpu().numpy()
+        soh, deg = h.get("soh").cpu().numpy(), h.get("last_deg").cpu().numpy()
+        obs = self._obs.cpu().numpy()
+        act = actions.detach().cpu().numpy() if torch.is_tensor(actions) else np.asarray(actions)
+        act = act.reshape(self.num_envs, self.num_cars)
+        pm = float(self.built.consts.price_multiplier)
+        hour, minute = self.built.tables["hour"], self.built.tables["minute"]
+        for i in idx:
+            if done[i]:                       # the reference logs nothing for the finishing step; the auto-reset logs its row
+                continue
+            ti = int(t[i])
+            trig = bool(self.built.consts.calc_degradation) and hour[ti] == 14 and minute[ti] == 45
+            rows = self._log_rows[i]
+            rows.append({"Episode": len(rows) // int(self.built.consts.episode_steps) + 1,
+                         "Time": pd.Timestamp(self.built.dates[ti]), "Observation": obs[i].copy(), "Action": act[i].copy(),
+                         "Reward": float(rew[i]), "Cashflow": float(cash[i]), "Penalties": float(rew[i] - cash[i] * pm),
+                         "Grid overloading": float(ovl[i]), "SOC violation": float(viol[i]),
+                         "Degradation": deg[i].copy() if trig else 0.0,
+                         "Charging energy": np.full(self.num_cars, np.nan), "SOH": soh[i].copy()})
+        self._log_reset_rows([i for i in idx if done[i]])
 
     def baseline_actions(self, policy, out=None):
         """Actions [E, N] (float32, on the device) of one of the reference's rule-based benchmark policies at every env's
@@ -230,10 +287,15 @@ class FleetVecEnv:
         return out
 
     def _m_get_log(self, idx):
-        """The reference returns its per-step pandas log; the batched env keeps reduced episode statistics on the
-        device instead (the same columns summed over envs and steps)."""
-        st = self.stats()
-        return [pd.DataFrame([st]) for _ in idx]
+        """Per-step log of the envs selected with enable_log() in the reference's DataLogger columns; for other envs the
+        reduced episode statistics kept on the device (the same quantities summed over envs and steps)."""
+        out = []
+        for i in idx:
+            if i in self._log_rows:
+                out.append(pd.DataFrame(self._log_rows[i], columns=list(self.LOG_COLUMNS)))
+            else:
+                out.append(pd.DataFrame([self.stats()]))
+        return out
 
     # ---- statistics
     def stats(self, all_reduce=False):

@@ -91,3 +91,34 @@ def test_fleet_env_gym_api():
     with pytest.raises(TypeError):
         env.step(np.array([np.nan, 0, 0, 0], dtype=np.float32))
     env.close()
+
+
+def test_evaluation_log_columns_and_values():
+    """enable_log(): the reference's DataLogger rows (reset row, one row per non-terminal step) for chosen envs."""
+    from fleetrl_b200 import FleetVecEnv
+    cfg = default_config("lmd", time_picker="random", end_cutoff=10)
+    E = 8
+    env = FleetVecEnv(cfg, E, inputs=_inputs(), output="torch", env_id_offset=5, seed=3)
+    orc = OracleFleet(env.built.consts, env.built.tables, E, env_id_offset=5)
+    env.reset(); orc.reset()
+    env.enable_log(indices=[0, 3])
+    rng = np.random.default_rng(2)
+    rewards = {0: [], 3: []}
+    for s in range(130):
+        a = rng.uniform(-1, 1, (E, 6)).astype(np.float32)
+        env.step(torch.from_numpy(a).to(env.device))
+        _, o_rew, o_cash, o_done, _ = orc.step(a, want_terminal=True)
+        for i in (0, 3):
+            if not o_done[i]:
+                rewards[i].append((o_rew[i], o_cash[i]))
+    for i in (0, 3):
+        log = env.env_method("get_log", indices=[i])[0]
+        assert list(log.columns) == list(env.LOG_COLUMNS)
+        steps = log[log["Action"].map(lambda v: np.any(v != 0))]
+        assert len(steps) == len(rewards[i])
+        np.testing.assert_allclose(steps["Reward"].to_numpy(dtype=float), [r for r, _ in rewards[i]], rtol=1e-11, atol=1e-10)
+        np.testing.assert_allclose(steps["Cashflow"].to_numpy(dtype=float), [c for _, c in rewards[i]], rtol=1e-12, atol=1e-13)
+        assert len(log) == len(steps) + 2                 # the initial reset row and the one after the auto-reset
+        assert log["Episode"].iloc[0] == 1 and log["Episode"].iloc[-1] == 2
+        assert any(np.ndim(d) == 1 for d in log["Degradation"])   # the 14:45 row carries the per-vehicle degradation
+    env.close()
