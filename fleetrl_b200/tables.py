@@ -213,6 +213,43 @@ class BuiltFleet:
     consumption: np.ndarray = None
 
 
+CACHE_VERSION = 1
+
+
+def save_fleet(built: "BuiltFleet", path: str):
+    """Binary cache of a built fleet: the flattened tables, the scalar half of FleetConsts and what the
+    host wrappers need (dates, start ranges, company).  The reference rebuilds its `db` from the CSV files at every
+    construction (~10 s of pandas at N = 50); loading this file takes milliseconds and is independent of pandas."""
+    import dataclasses
+    import json
+    arrays = {f"t_{k}": v for k, v in built.tables.items() if v is not None}
+    meta = dict(version=CACHE_VERSION, consts=built.consts.to_dict(), company=dataclasses.asdict(built.company),
+                start_ranges={k: list(v) for k, v in built.start_ranges.items()},
+                absent=[k for k, v in built.tables.items() if v is None], cfg=built.rc.cfg)
+    np.savez_compressed(path, dates=np.asarray(built.dates).astype("datetime64[ns]").astype(np.int64),
+                        consumption=built.consumption if built.consumption is not None else np.zeros(0),
+                        meta=np.frombuffer(json.dumps(meta, default=str).encode(), dtype=np.uint8), **arrays)
+
+
+def load_fleet(path: str) -> "BuiltFleet":
+    """Inverse of save_fleet: tables and constants are restored bit for bit."""
+    import json
+    z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+    meta = json.loads(bytes(z["meta"]).decode())
+    if meta.get("version") != CACHE_VERSION:
+        raise ValueError(f"{path}: fleet cache version {meta.get('version')} != {CACHE_VERSION}")
+    tables = {k[2:]: z[k] for k in z.files if k.startswith("t_")}
+    for k in meta["absent"]:
+        tables[k] = None
+    cfg = meta["cfg"]
+    rc = _config.resolve(cfg) if all(k in cfg for k in _config.MANDATORY_KEYS) else None
+    cons = z["consumption"]
+    return BuiltFleet(consts=FleetConsts.from_dict(meta["consts"]), tables=tables,
+                      dates=z["dates"].astype("datetime64[ns]"), company=_config.Company(**meta["company"]), rc=rc,
+                      start_ranges={k: tuple(v) for k, v in meta["start_ranges"].items()},
+                      consumption=cons if cons.size else None)
+
+
 def start_index_ranges(dates, time_conf, static_start="01/02/2021 19:00"):
     """Candidate start indices of the three time pickers (time_picker/*.py)."""
     idx = pd.DatetimeIndex(dates)

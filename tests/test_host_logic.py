@@ -121,3 +121,27 @@ def test_generator_and_builder_invariants(use_case):
     prc = tb["price_reward_curve"]
     jan = prc[: 31 * 96]
     assert abs(jan.mean() - prc.mean()) < 1e-9
+
+
+def test_fleet_cache_roundtrip(tmp_path):
+    """save_fleet / load_fleet (binary cache of the flattened tables): constants and tables restored bit for bit."""
+    from fleetrl_b200.config import default_config
+    from fleetrl_b200.schedule import generate_schedule, synthetic_series
+    from fleetrl_b200.tables import FleetInputs, build_fleet, load_fleet, save_fleet
+    sched = generate_schedule("lmd", 3, start="2020-01-01 00:00", end="2020-02-29 23:59", seed=4)
+    price, tariff, load, pv = synthetic_series(start="2020-01-01 00:00", end="2020-02-29 23:59")
+    cfg = default_config("lmd", end_cutoff=10, include_pv=False)
+    built = build_fleet(cfg, FleetInputs(sched, price, tariff, load, pv))
+    path = str(tmp_path / "fleet_cache")
+    save_fleet(built, path)
+    back = load_fleet(path)
+    assert back.consts.to_dict() == built.consts.to_dict()
+    assert set(back.tables) == set(built.tables)
+    for k, v in built.tables.items():
+        if v is None:
+            assert back.tables[k] is None
+        else:
+            assert back.tables[k].dtype == v.dtype
+            np.testing.assert_array_equal(back.tables[k], v)
+    np.testing.assert_array_equal(back.dates, built.dates)
+    assert back.start_ranges == built.start_ranges and back.company == built.company
