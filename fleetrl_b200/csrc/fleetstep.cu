@@ -862,9 +862,12 @@ struct PfEnv {   // per-env scratch of a tile (shared memory, triple buffered)
     double S, F_cr, F_dr, Rfac, pv_share, gml, pvv;
 };
 
+#ifndef KPFSTAGES
+#define KPFSTAGES 2
+#endif
 // input stage of the pf kernel: the per-slot inputs of one tile, structure of arrays indexed by the slot's thread
 constexpr int kPfStA32 = 0, kPfStHl = 1024, kPfStHv = 2048, kPfStSoc = 3072, kPfStSoh = 5120, kPfStSdeg = 7168,
-              kPfStR0 = 9216, kPfStR1 = 13312, kPfStageBytes = 17408, kPfStages = 2;
+              kPfStR0 = 9216, kPfStR1 = 13312, kPfStageBytes = 17408, kPfStages = KPFSTAGES;
 // measured on B200 at cfg2: 2 CTAs/SM x 10 warps with ~100 registers (no spills, L1 left for the tables) beat 3 CTAs/SM
 // at 64 registers by 5-6 %
 #ifndef KPFOUT
@@ -893,12 +896,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    // the suspend-time hint (ns) only bounds how long the hardware may park the thread before it re-checks; the thread
+    // resumes as soon as the phase completes, so a generous hint just means fewer spin iterations in the issue slots
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -1179,18 +1184,14 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
         }
         cp_async_commit();
     };
-    {
-        const int2 ev0 = load_env2(tile0);
-        const int2 ev1 = load_env2(tile0 + G);
-        issue_copies(tile0, ev0, 0);
-        issue_copies(tile0 + G, ev1, 1);
-    }
+#pragma unroll
+    for (int q = 0; q < kPfStages; q++) issue_copies(tile0 + q * G, load_env2(tile0 + q * G), q);
 
     int it = 0;
     PF_DECL();
     PF_START();
     for (int tile = tile0; tile < ntiles; tile += G, it++) {
-        const int buf = it % kPfOut, stg = it & 1;
+        const int buf = it % kPfOut, stg = it % kPfStages;
         const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % kPfEnvs) * p.pf_envs_b);
         double* contrib = reinterpret_cast<double*>(contrib0 + buf * p.pf_contrib_b);
         float* obs_tile = reinterpret_cast<float*>(obs0 + buf * p.pf_obs_b);
@@ -1200,8 +1201,8 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
 
         // ---- this tile's inputs: wait for the thread's own copies; they are read from the stage where they are needed
         // and the stage is refilled (for the tile after next) at the end of the tile, one tile period ahead of its use
-        const int2 ev_next = load_env2(tile + 2 * G);
-        cp_async_wait_group<1>();
+        const int2 ev_next = load_env2(tile + kPfStages * G);
+        cp_async_wait_group<kPfStages - 1>();
         const unsigned char* stp = smem_raw + p.pf_off_stage + stg * kPfStageBytes;
         PF_MARK(4);
         mbar_wait(&bar_env[it % kPfEnvs], (uint32_t)((it / kPfEnvs) & 1));   // env scratch of this tile is staged
@@ -1334,7 +1335,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             __stcs(p.hl + i, o_hl);
             __stcs(p.hist + o_hist, o_sdeg);
         }
-        issue_copies(tile + 2 * G, ev_next, stg);             // refill the stage this tile has just consumed
+        issue_copies(tile + kPfStages * G, ev_next, stg);     // refill the stage this tile has just consumed
         PF_MARK(3);
     }
     PF_FLUSH(8);
