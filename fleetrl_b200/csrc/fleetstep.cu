@@ -130,6 +130,7 @@ struct StepParams {
     unsigned int* wl_done;    // [1]
     // persistent step kernel geometry (host-computed so that the kernel reads it from the constant bank, not registers)
     int pf_ntiles, pf_cslots, pf_cper, pf_pair;
+    unsigned int pf_tile_hist;                                // B * RN: history elements per tile (< 2^32, checked at create)
     int pf_envs_b, pf_contrib_b, pf_obs_b;                    // bytes of one env-scratch / contribution / obs buffer
     int pf_off_contrib, pf_off_sums, pf_off_obs, pf_off_stage;   // shared-memory offsets
     int po_nc, po_lp, po_g;   // cooperative post kernel: vehicles per chunk, column pitch (odd), threads per vehicle in pass 2
@@ -914,6 +915,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // pf kernel hand-offs are mbarriers (not named barriers): a waiting warp then depends only on the producer of what it
 // waits for, never on its sibling compute warps, so the eight compute warps drift apart by up to a tile and their
 // per-tile imbalance (charging / discharging / absent vehicles) averages out instead of adding up.
+#ifdef PF_NOSTATS
+#define PF_STAT_ADD(ptr, v) do { (void)(ptr); (void)(v); } while (0)
+#else
+#define PF_STAT_ADD(ptr, v) atomicAdd(ptr, v)
+#endif
 #ifdef PF_TIMING
 __device__ unsigned long long g_pf_clk[16];
 #define PF_MARK(k) do { const long long _c = clock64(); _acc[(k) & 7] += (unsigned long long)(_c - _pt); _pt = _c; } while (0)
@@ -1109,19 +1115,19 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
                     const double rel = overload / p.grid + 1;                                      // fleet_environment.py:496
                     const double pen = (rel < 1.1) ? 0.0 : -700 / (1 + exp(-15.77350877 * (rel - 1.33298382)));
                     reward += pen * p.pen_ovl;                                                     // score_config.py:33-41
-                    atomicAdd(stt + FLEET_S_OVERLOAD_KW, overload);
+                    PF_STAT_ADD(stt + FLEET_S_OVERLOAD_KW, overload);
                 }
                 const double soc_viol = fabs(sums_r[Q_MISS * B + bb]);
                 const double n_viol = sums_r[Q_NVIOL * B + bb];
                 const int dn = (es.flags & EF_DONE) ? 1 : 0;
                 const double ep_ret = ((bb == lane) ? ep_prev : p.env_f64[(size_t)EF_EP_RETURN * p.E + e]) + reward;
-                atomicAdd(stt + FLEET_S_STEPS, 1.0);
-                atomicAdd(stt + FLEET_S_REWARD, reward);
-                atomicAdd(stt + FLEET_S_CASHFLOW, cashflow);
-                if (n_viol > 0) { atomicAdd(stt + FLEET_S_SOC_VIOL, soc_viol); atomicAdd(stt + FLEET_S_N_VIOL, n_viol); }
+                PF_STAT_ADD(stt + FLEET_S_STEPS, 1.0);
+                PF_STAT_ADD(stt + FLEET_S_REWARD, reward);
+                PF_STAT_ADD(stt + FLEET_S_CASHFLOW, cashflow);
+                if (n_viol > 0) { PF_STAT_ADD(stt + FLEET_S_SOC_VIOL, soc_viol); PF_STAT_ADD(stt + FLEET_S_N_VIOL, n_viol); }
                 if (dn) {
-                    atomicAdd(stt + FLEET_S_EPISODES, 1.0);
-                    atomicAdd(stt + FLEET_S_EP_RETURN, ep_ret);
+                    PF_STAT_ADD(stt + FLEET_S_EPISODES, 1.0);
+                    PF_STAT_ADD(stt + FLEET_S_EP_RETURN, ep_ret);
                     p.env_f64[(size_t)EF_LAST_EP_RETURN * p.E + e] = ep_ret;
                 }
                 p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
@@ -1156,6 +1162,8 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
     // is what the HBM latency x bandwidth product asks for (a register pipeline one tile deep was latency bound), and
     // since every thread reads back only what it copied itself no barrier is involved, just cp.async.wait_group.
     const uint32_t stage0 = smem_u32(smem_raw + p.pf_off_stage);
+    const uint64_t stream = l2_evict_first_policy();          // (keep: created at the top of the kernel)
+    const size_t hist_slot = (size_t)b * p.RN + n;            // this slot's offset inside its tile's history block
     auto load_env2 = [&](int tile) -> int2 {
         const int e = tile * B + b;
         int2 v = make_int2(0, 0);
@@ -1169,7 +1177,6 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
         if (slot && tile < ntiles && e < p.E) {
             const size_t i = (size_t)tile * cstride + j;
             const uint32_t st = stage0 + (uint32_t)stage * kPfStageBytes;
-            const uint64_t stream = l2_evict_first_policy(), keep = l2_evict_last_policy();   // made here: not held in registers
             const int k = ev.x - ev.y;
             const int t1 = min(ev.x + 1, p.T - 1);
             const int4* rp = reinterpret_cast<const int4*>(p.ev_rec + (size_t)t1 * N + n);
@@ -1177,7 +1184,8 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             cp_async8_hint(st + kPfStSoc + j * 8, p.soc + i, stream);
             cp_async4_hint(st + kPfStHl + j * 4, p.hl + i, stream);
             cp_async8_hint(st + kPfStSoh + j * 8, p.soh + i, stream);
-            cp_async8_hint(st + kPfStSdeg + j * 8, p.hist + (size_t)e * p.RN + (unsigned)((p.calc_deg ? k : (k & 1)) * N + n), stream);
+            cp_async8_hint(st + kPfStSdeg + j * 8,
+                           p.hist + ((size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)((p.calc_deg ? k : (k & 1)) * N)), stream);
             cp_async16_hint(st + kPfStR0 + j * 16, rp, keep);
             cp_async16_hint(st + kPfStR1 + j * 16, rp + 1, keep);
             if (n < H) cp_async4_hint(st + kPfStHv + j * 4, p.hdr + (size_t)t1 * p.hdr_stride + n, keep);
@@ -1187,12 +1195,13 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
 #pragma unroll
     for (int q = 0; q < kPfStages; q++) issue_copies(tile0 + q * G, load_env2(tile0 + q * G), q);
 
-    int it = 0;
+    // rotating buffer indices and mbarrier phase bits (no division in the loop)
+    int it = 0, buf = 0, stg = 0, ebuf = 0;
+    uint32_t ph_env = 0, ph_free = 0;                          // parity to wait for on bar_env[ebuf] / bar_free[buf]
     PF_DECL();
     PF_START();
     for (int tile = tile0; tile < ntiles; tile += G, it++) {
-        const int buf = it % kPfOut, stg = it % kPfStages;
-        const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % kPfEnvs) * p.pf_envs_b);
+        const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + ebuf * p.pf_envs_b);
         double* contrib = reinterpret_cast<double*>(contrib0 + buf * p.pf_contrib_b);
         float* obs_tile = reinterpret_cast<float*>(obs0 + buf * p.pf_obs_b);
         const int e0 = tile * B;
@@ -1205,10 +1214,10 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
         cp_async_wait_group<kPfStages - 1>();
         const unsigned char* stp = smem_raw + p.pf_off_stage + stg * kPfStageBytes;
         PF_MARK(4);
-        mbar_wait(&bar_env[it % kPfEnvs], (uint32_t)((it / kPfEnvs) & 1));   // env scratch of this tile is staged
+        mbar_wait(&bar_env[ebuf], ph_env);                    // env scratch of this tile is staged
         PF_SETTLE();
         PF_MARK(0);
-        if (it >= kPfOut) mbar_wait(&bar_free[buf], (uint32_t)(((it / kPfOut) - 1) & 1));   // contribution + obs buffers are free again
+        if (it >= kPfOut) mbar_wait(&bar_free[buf], ph_free);  // contribution + obs buffers are free again
         PF_SETTLE();
         PF_MARK(2);
 
@@ -1237,6 +1246,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             const int there = rec.there_prev;                               // db.There at t
             const double a = (double)reinterpret_cast<const float*>(stp + kPfStA32)[j];
             double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
+#ifndef PF_NOMATH
             double num = 0;
             if (a >= 0) {                                                   // ev_charger.py:98-156
                 const double dem = (tgt - soc) * cap;
@@ -1290,10 +1300,13 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
                 p.tflip[i] = 1;
                 atomicAdd(p.n_flips, 1);
             }
+#else  /* diagnostic build: same loads and stores, almost no arithmetic */
+            double num = a; soc = soc + a * 1e-3; c_cr = a; c_miss = soh; const double c_ath = a; const float ntl = rec.tl; if (ntl != 0.f) hl = ntl; (void)num; (void)tgt; (void)cap; (void)there;
+#endif
             if (hl != 0.f) sdeg = soc;                                      // :621-623
 
             o_soc = soc; o_hl = hl; o_sdeg = sdeg;
-            o_hist = (size_t)(e0 + b) * p.RN + (unsigned)((p.calc_deg ? k + 1 : ((k + 1) & 1)) * N + n);
+            o_hist = (size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)((p.calc_deg ? k + 1 : ((k + 1) & 1)) * N);
             q_rew = c_cr + c_dr + c_inv + c_oc + c_dep;
             q_cash = -1 * c_cost + c_rev;
             q_ath = c_ath; q_miss = c_miss; q_nviol = c_nviol;
@@ -1337,6 +1350,9 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
         }
         issue_copies(tile + kPfStages * G, ev_next, stg);     // refill the stage this tile has just consumed
         PF_MARK(3);
+        if (++stg == kPfStages) stg = 0;
+        if (++ebuf == kPfEnvs) { ebuf = 0; ph_env ^= 1u; }
+        if (++buf == kPfOut) { buf = 0; if (it >= kPfOut) ph_free ^= 1u; }
     }
     PF_FLUSH(8);
 }
@@ -2746,6 +2762,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
                 h->smem_pf = smpf;
                 const int ntiles = (E + p.B - 1) / p.B;
                 p.pf_ntiles = ntiles;
+                p.pf_tile_hist = (unsigned int)((size_t)p.B * p.RN);
                 p.pf_pair = (N & 1) ? 0 : 1;
                 p.pf_cslots = pf_contrib_slots(p.B, N);
                 p.pf_cper = p.pf_pair ? N / 2 : N;

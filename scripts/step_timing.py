@@ -22,6 +22,7 @@ stream = torch.cuda.current_stream(dev); sp = stream.cuda_stream
 ptrs = [a.data_ptr() for a in ring]
 K = 320
 evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+h.set_timing(True)
 t0 = time.perf_counter()
 evs[0].record(stream)
 for s in range(K):
@@ -34,3 +35,5 @@ print("cpu enqueue per step us:", t_cpu / K * 1e6)
 print("per-step ms: min %.4f median %.4f mean %.4f max %.4f" % (ms.min(), np.median(ms), ms.mean(), ms.max()))
 print("slowest steps:", np.argsort(-ms)[:6], np.sort(-ms)[:6] * -1)
 print("steps 100..120:", np.round(ms[100:120], 3))
+a, b, n = h.get_timing()
+print("kernel split (CUDA events inside the library): step kernel %.4f ms, post kernel %.4f ms per step over %d steps" % (a / n, b / n, n))
