@@ -129,7 +129,7 @@ struct StepParams {
     int* wl_count;            // [4] {degradation entries, reset-only entries, next degradation entry, next reset entry}
     unsigned int* wl_done;    // [1]
     // persistent step kernel geometry (host-computed so that the kernel reads it from the constant bank, not registers)
-    int pf_ntiles, pf_cslots, pf_cper, pf_pair;
+    int pf_B, pf_bulk, pf_ntiles, pf_cslots, pf_cper, pf_pair;      // pf_B: envs per tile = kPfCompute / N
     unsigned int pf_tile_hist;                                // B * RN: history elements per tile (< 2^32, checked at create)
     int pf_envs_b, pf_contrib_b, pf_obs_b;                    // bytes of one env-scratch / contribution / obs buffer
     int pf_off_contrib, pf_off_sums, pf_off_obs, pf_off_stage;   // shared-memory offsets
@@ -855,7 +855,10 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
 //  * no CTA-wide barrier in the loop: producer/consumer hand-offs use named barriers (bar.arrive / bar.sync) on
 //    double-buffered contribution + observation tiles and triple-buffered env scratch.
 // Selected when auto_reset is on and 8 <= N <= 256 (one pass per tile); otherwise the generic kernel runs.
-constexpr int kPfCompute = 256;
+#ifndef KPFCOMPUTE
+#define KPFCOMPUTE 256
+#endif
+constexpr int kPfCompute = KPFCOMPUTE;           // compute threads (one per slot of a tile)
 constexpr int kPfThreads = kPfCompute + 64;     // + two epilogue warps
 
 struct PfEnv {   // per-env scratch of a tile (shared memory, triple buffered)
@@ -867,8 +870,9 @@ struct PfEnv {   // per-env scratch of a tile (shared memory, triple buffered)
 #define KPFSTAGES 2
 #endif
 // input stage of the pf kernel: the per-slot inputs of one tile, structure of arrays indexed by the slot's thread
-constexpr int kPfStA32 = 0, kPfStHl = 1024, kPfStHv = 2048, kPfStSoc = 3072, kPfStSoh = 5120, kPfStSdeg = 7168,
-              kPfStR0 = 9216, kPfStR1 = 13312, kPfStageBytes = 17408, kPfStages = KPFSTAGES;
+constexpr int kPfStA32 = 0, kPfStHl = 4 * KPFCOMPUTE, kPfStHv = 8 * KPFCOMPUTE, kPfStSoc = 12 * KPFCOMPUTE,
+              kPfStSoh = 20 * KPFCOMPUTE, kPfStSdeg = 28 * KPFCOMPUTE, kPfStR0 = 36 * KPFCOMPUTE, kPfStR1 = 52 * KPFCOMPUTE,
+              kPfStageBytes = 68 * KPFCOMPUTE, kPfStages = KPFSTAGES;
 // measured on B200 at cfg2: 2 CTAs/SM x 10 warps with ~100 registers (no spills, L1 left for the tables) beat 3 CTAs/SM
 // at 64 registers by 5-6 %
 #ifndef KPFOUT
@@ -937,7 +941,7 @@ __device__ unsigned long long g_pf_clk[16];
 template <bool kNorm, bool kAux>
 __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = p.N, B = p.B, D = p.D;
+    const int N = p.N, B = p.pf_B, D = p.D;
     const int cstride = B * N;
     const bool pair = p.pf_pair != 0;                        // contributions of vehicle pairs are pre-added (even N)
     const int cslots = p.pf_cslots;                          // contribution entries per quantity and tile
@@ -989,11 +993,11 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             PF_MARK(1);
 
             // ---- observation tile -> HBM
-            const bool use_bulk = p.bulk_ok && nb == B && !s_any_reset[it % kPfEnvs] && p.obs != nullptr;
+            const bool use_bulk = p.pf_bulk && nb == B && !s_any_reset[it % kPfEnvs] && p.obs != nullptr;
             if (use_bulk) {
                 // the writers have run fence.proxy.async before arriving on bar_done: no second fence here
                 if (lane == 0) bulk_store_s2g_nofence(p.obs + (size_t)e0 * D, obs_tile, (uint32_t)(B * D * 4));
-            } else if (p.bulk_ok && (D & 3) == 0) {
+            } else if (p.pf_bulk && (D & 3) == 0) {
                 // rows of finishing envs go to terminal_obs: one bulk store per env row (D*4 bytes, 16-byte aligned)
                 if (lane < nb) {
                     const int e = e0 + lane;
@@ -1026,7 +1030,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_sums_ready[sbuf]);
             PF_MARK(2);
-            if (p.bulk_ok && (use_bulk ? lane == 0 : (lane < nb && (D & 3) == 0))) bulk_store_wait_read();
+            if (p.pf_bulk && (use_bulk ? lane == 0 : (lane < nb && (D & 3) == 0))) bulk_store_wait_read();
             __syncwarp();
             PF_MARK(3);
             if (lane == 0) mbar_arrive(&bar_free[buf]);       // contribution + obs buffers of this tile are free again
@@ -1338,8 +1342,10 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             contrib[Q_MISS * cslots + cj] = q_miss;
             contrib[Q_NVIOL * cslots + cj] = q_nviol;
         }
+        PF_MARK(1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (bulk store)
         mbar_arrive(&bar_done[buf]);
+        PF_MARK(5);
         // the new state goes to HBM after the hand-off: the fence above (MEMBAR + proxy fence) then only has shared-memory
         // stores to wait for, not these
         if (active) {
@@ -1348,6 +1354,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             __stcs(p.hl + i, o_hl);
             __stcs(p.hist + o_hist, o_sdeg);
         }
+        PF_MARK(6);
         issue_copies(tile + kPfStages * G, ev_next, stg);     // refill the stage this tile has just consumed
         PF_MARK(3);
         if (++stg == kPfStages) stg = 0;
@@ -2753,25 +2760,28 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     {
         const char* force = getenv("FLEETSTEP_KERNEL");   // "generic" / "pf" / "tma"; default: pf when applicable
         const bool want = !force || strcmp(force, "pf") == 0;
-        if (want && c.auto_reset && N >= 8 && p.B * N <= kPfThreads) {
-            const size_t smpf = pf_smem_bytes(p.B, N, h->D);
+        const int pfB = kPfCompute / N;
+        if (want && c.auto_reset && N >= 8 && pfB >= 1 && pfB <= 32) {   // the epilogue warps use one lane per env of a tile
+            const size_t smpf = pf_smem_bytes(pfB, N, h->D);
             int per_sm = 0;
             if ((int64_t)smpf <= (int64_t)h->max_smem_optin &&
                 cudaFuncSetAttribute(pick_pf(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smpf) == cudaSuccess &&
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_pf(h), kPfThreads, smpf) == cudaSuccess && per_sm >= 1) {
                 h->smem_pf = smpf;
-                const int ntiles = (E + p.B - 1) / p.B;
+                const int ntiles = (E + pfB - 1) / pfB;
+                p.pf_B = pfB;
+                p.pf_bulk = ((pfB * h->D) % 4 == 0) ? 1 : 0;
                 p.pf_ntiles = ntiles;
-                p.pf_tile_hist = (unsigned int)((size_t)p.B * p.RN);
+                p.pf_tile_hist = (unsigned int)((size_t)pfB * p.RN);
                 p.pf_pair = (N & 1) ? 0 : 1;
-                p.pf_cslots = pf_contrib_slots(p.B, N);
+                p.pf_cslots = pf_contrib_slots(pfB, N);
                 p.pf_cper = p.pf_pair ? N / 2 : N;
-                p.pf_envs_b = (int)align16((size_t)p.B * sizeof(PfEnv));
+                p.pf_envs_b = (int)align16((size_t)pfB * sizeof(PfEnv));
                 p.pf_contrib_b = (int)align16((size_t)kNQ * p.pf_cslots * 8);
-                p.pf_obs_b = (int)align16((size_t)p.B * h->D * 4);
+                p.pf_obs_b = (int)align16((size_t)pfB * h->D * 4);
                 p.pf_off_contrib = kPfEnvs * p.pf_envs_b;
                 p.pf_off_sums = p.pf_off_contrib + kPfOut * p.pf_contrib_b;
-                p.pf_off_obs = p.pf_off_sums + 2 * (int)align16((size_t)kNQ * p.B * 8);
+                p.pf_off_obs = p.pf_off_sums + 2 * (int)align16((size_t)kNQ * pfB * 8);
                 p.pf_off_stage = (int)align16((size_t)p.pf_off_obs + (size_t)kPfOut * p.pf_obs_b);
                 const int g = prop.multiProcessorCount * per_sm;
                 h->grid_pf = g < ntiles ? g : ntiles;
@@ -2844,7 +2854,7 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     CUDA_TRY(h, cudaSetDevice(h->device));
     StepParams p = h->p;
     p.actions = actions_dev; p.obs = obs_dev; p.reward = reward_dev; p.done = done_dev; p.terminal_obs = terminal_obs_dev;
-    if ((((uintptr_t)obs_dev) | ((uintptr_t)terminal_obs_dev)) & 15) p.bulk_ok = 0;   // bulk stores need 16-byte aligned rows
+    if ((((uintptr_t)obs_dev) | ((uintptr_t)terminal_obs_dev)) & 15) { p.bulk_ok = 0; p.pf_bulk = 0; }   // bulk stores need 16-byte aligned rows
     cudaEvent_t* tev = nullptr;
     if (h->timing && !h->tev.empty()) tev = &h->tev[(size_t)(h->tcount % kTimingRing) * 3];
     if (tev) cudaEventRecord(tev[0], (cudaStream_t)stream);

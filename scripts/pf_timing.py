@@ -32,6 +32,6 @@ print("epilogue detail: any_reset %.0f | bulk store issue %.0f" % (v[7] / (K * n
 ep = v[:6] / (K * ntiles)
 print("epilogue warp, cycles per tile: pre-Done %.0f | wait Done %.0f | store+sums %.0f | wait_read %.0f | stage_env+arrive %.0f | finalise %.0f | total %.0f"
       % (*ep, ep.sum()))
-cw = v[[8, 10, 11, 12]] / (K * ntiles * 8)
-print("compute warps, cycles per tile: wait Env %.0f | wait Free %.0f | compute %.0f | issue next loads %.0f | total %.0f" % (*cw, cw.sum()))
+cw = v[[12, 8, 10, 9, 13, 14, 11]] / (K * ntiles * 8)
+print("compute warps, cycles per tile: loop top + wait own copies %.0f | wait Env %.0f | wait Free %.0f | body (math, smem stores) %.0f | proxy fence + arrive %.0f | state stores %.0f | issue copies %.0f | total %.0f" % (*cw, cw.sum()))
 print("epilogue warps by (%warpid & 3), summed over the launches:", v[12:16] / K)
