@@ -133,6 +133,8 @@ struct StepParams {
     unsigned int pf_tile_hist;                                // B * RN: history elements per tile (< 2^32, checked at create)
     int pf_envs_b, pf_contrib_b, pf_obs_b;                    // bytes of one env-scratch / contribution / obs buffer
     int pf_off_contrib, pf_off_sums, pf_off_obs, pf_off_stage;   // shared-memory offsets
+    int po_nch;               // chunks (work items) per degradation entry: vehicles [k*po_nc, (k+1)*po_nc)
+    int* wl_chunk_cnt;        // [E] finished chunks per entry (only for entries that also reset)
     int po_nc, po_lp, po_g;   // cooperative post kernel: vehicles per chunk, column pitch (odd), threads per vehicle in pass 2
     int po_stk, po_recs, po_misc;   // its shared-memory offsets (bytes)
     double* post_scratch_v;   // [grid_post][scratch_cap][64] fallback rainflow value ring
@@ -1868,6 +1870,7 @@ __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepPara
 #define KPOST2_BWARPS 8
 #endif
 constexpr int kPost2Threads = 256;
+constexpr int kPost2DefaultChunks = 1;   // vehicle chunks per degradation entry (FLEETSTEP_POST_CHUNKS overrides)
 
 struct Post2Misc {   // per-chunk scalars in shared memory
     double part[kPost2Threads];
@@ -1885,12 +1888,14 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
     int* s_m = reinterpret_cast<int*>(misc + 1);                           // [NC] cycles found
     int* s_rfl = s_m + NC;                                                 // [NC] rainflow_length of the vehicle
     double* s_msum = reinterpret_cast<double*>(s_rfl + NC);                // [NC] sum of cycle means (2*NC ints before it)
-    __shared__ int s_w;
+    __shared__ int s_w, s_last;
     __shared__ int2 s_ent;
     __shared__ int4 s_ev;
     __shared__ double s_deg;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int count_d = p.wl_count[0], count_r = p.wl_count[1];
+    const int nch = p.po_nch;                            // work items per entry (vehicle chunks spread over CTAs)
+    const int items = count_d * nch;
     const double alpha_sei = 5.75E-2, beta_sei = 121, k_sigma = 1.04, sigma_ref = 0.5, k_temp = 6.93E-2,
                  temp_ref = 25, k_dt = 4.14E-10, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
     PT_START();
@@ -1899,12 +1904,13 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
     // entry's list record and env4 while the current one is processed, so the two dependent round trips are hidden.
     if (tid == 0) {
         s_w = blockIdx.x; s_deg = 0;
-        if (s_w < count_d) { s_ent = p.wl[s_w]; s_ev = p.env4[s_ent.x]; }
+        if (s_w < items) { s_ent = p.wl[s_w / nch]; s_ev = p.env4[s_ent.x]; }
     }
     for (;;) {
         __syncthreads();
         const int w = s_w;
-        if (w >= count_d) break;
+        if (w >= items) break;
+        const int entry = w / nch, chunk = w - entry * nch;
         const int2 ent = s_ent;
         const int e = ent.x, wf = ent.y;
         const int4 ev = s_ev;                           // {t (already advanced), t_start, ep_count}
@@ -1914,11 +1920,11 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
         int4 ev_next = make_int4(0, 0, 0, 0);
         if (tid == 0) {
             w_next = atomicAdd(p.wl_count + 2, 1) + (int)gridDim.x;
-            if (w_next < count_d) { ent_next = p.wl[w_next]; ev_next = p.env4[ent_next.x]; }
+            if (w_next < items) { ent_next = p.wl[w_next / nch]; ev_next = p.env4[ent_next.x]; }
         }
         const double* hbase = p.hist + (size_t)e * p.R * N;
 
-        if (p.deg_mode == FLEET_DEG_EMPIRICAL) {
+        if (p.deg_mode == FLEET_DEG_EMPIRICAL) {           // (one item per entry in this mode)
             for (int n = tid; n < N; n += kPost2Threads) {
                 const size_t ii = (size_t)e * N + n;
                 const double deg = empirical_eval(p.dt, p.evse, N, hbase + n, len);
@@ -1928,7 +1934,7 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
                 if (deg != 0) atomicAdd(&s_deg, deg);
             }
         } else {
-            for (int n0 = 0; n0 < N; n0 += NC) {
+            for (int n0 = chunk * NC; n0 < min(N, (chunk + 1) * NC); n0 += NC) {   // this item's vehicles (one pass)
                 const int nc = min(NC, N - n0);
                 // ---- stage the chunk: coalesced along vehicles in HBM, one column per vehicle in shared memory;
                 // 8-byte cp.async copies, all in flight at once (one HBM round trip for the whole history)
@@ -2133,7 +2139,15 @@ __global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepPa
         __syncthreads();
         if (tid == 0 && s_deg != 0)
             atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
-        if (wf & WL_RESET) post_reset_env<kNorm, kAux>(p, e, ev, tid, kPost2Threads);
+        if (wf & WL_RESET) {       // the env also finished: the CTA that completes its last chunk resets it
+            if (tid == 0) {
+                __threadfence();
+                s_last = (nch == 1) || (atomicAdd(&p.wl_chunk_cnt[entry], 1) == nch - 1);
+                if (s_last && nch > 1) p.wl_chunk_cnt[entry] = 0;
+            }
+            __syncthreads();
+            if (s_last) { __threadfence(); post_reset_env<kNorm, kAux>(p, e, ev, tid, kPost2Threads); }
+        }
         __syncthreads();                                             // everybody has read s_w / s_ent / s_ev / s_deg
         if (tid == 0) { s_w = w_next; s_ent = ent_next; s_ev = ev_next; s_deg = 0; }
         PT_MARK(5);
@@ -2651,6 +2665,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     if ((rc = dev_alloc(h, &p.err_flags, (size_t)4))) return rc;
     if ((rc = dev_alloc(h, &p.wl, (size_t)E))) return rc;
     if ((rc = dev_alloc(h, &p.wlr, (size_t)E))) return rc;
+    if ((rc = dev_alloc(h, &p.wl_chunk_cnt, (size_t)E))) return rc;
     if ((rc = dev_alloc(h, &p.wl_count, (size_t)4))) return rc;
     if ((rc = dev_alloc(h, &p.wl_done, (size_t)4))) return rc;
 
@@ -2738,10 +2753,21 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
         if (nc < (N < 8 ? N : 8)) nc = fit((size_t)h->max_smem_optin);
         if (nc > N) nc = N;
         if (nc > kPost2Threads) nc = kPost2Threads;
+        // An entry's vehicles are split into chunks that different CTAs process concurrently: smaller CTAs' worth of
+        // shared memory -> more resident work items per SM, and the per-item latency (staging, reversal detection,
+        // stress) shrinks with the chunk; the serial three-point stack of the slowest vehicle stays the critical path.
+        {
+            const char* ck = getenv("FLEETSTEP_POST_CHUNKS");
+            int want = ck ? atoi(ck) : kPost2DefaultChunks;
+            if (want < 1) want = 1;
+            const int64_t per = (N + want - 1) / want;
+            if (per >= 1 && per < nc) nc = per;
+        }
         const bool sei = c.calc_degradation && c.deg_mode == FLEET_DEG_SEI;
         if ((!force || strcmp(force, "v1") != 0) && h->need_post && (nc >= 1 || !sei)) {
             if (!sei) nc = 1;
             p.po_nc = (int)nc; p.po_lp = LP; p.po_g = kPost2Threads / (int)nc;
+            p.po_nch = sei ? (int)((N + nc - 1) / nc) : 1;
             p.po_stk = (int)align16((size_t)nc * LP * 8);
             p.po_recs = (int)align16((size_t)p.po_stk + (size_t)nc * LP * 2);
             p.po_misc = (int)align16((size_t)p.po_recs + (size_t)nc * LP * 4);
@@ -2751,7 +2777,8 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
             CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post2(h), kPost2Threads, h->smem_post2));
             if (per_sm < 1) per_sm = 1;
             const int64_t g = (int64_t)h->num_sms * per_sm;
-            h->grid_post2 = (int)(g < E ? g : E);
+            const int64_t max_items = (int64_t)E * p.po_nch;
+            h->grid_post2 = (int)(g < max_items ? g : max_items);
             h->use_post2 = 1;
         }
     }

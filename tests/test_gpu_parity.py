@@ -43,7 +43,10 @@ KERNELS = ([(n, "pf") for n in sorted(CASES) if CASES[n]["n_evs"] >= 8 and CASES
            + [(n, "generic") for n in sorted(CASES)] + [(n, "tma") for n in ("lmd_50ev_e36", "ut_10ev_e50")]
            # the thread-per-vehicle post kernel (FLEETSTEP_POST=v1) that the cooperative one falls back to
            + [(n, "generic+postv1") for n in ("lmd_50ev", "ct_20ev_two_trips", "lmd_300ev", "lmd_9ev_norm_nocarry",
-                                              "lmd_1ev")])
+                                              "lmd_1ev")]
+           # vehicle chunks of a degradation entry spread over CTAs (FLEETSTEP_POST_CHUNKS)
+           + [(n, "pf+chunks3") for n in ("lmd_50ev", "ct_20ev_two_trips", "lmd_9ev_norm_nocarry")]
+           + [("lmd_300ev", "generic+chunks2"), ("lmd_7ev", "generic+chunks7")])
 
 
 @pytest.mark.parametrize("name,kernel", KERNELS)
@@ -54,6 +57,10 @@ def test_gpu_vs_oracle(name, kernel, monkeypatch):
         monkeypatch.setenv("FLEETSTEP_POST", "v1")
     else:
         monkeypatch.delenv("FLEETSTEP_POST", raising=False)
+    if "+chunks" in kernel:
+        monkeypatch.setenv("FLEETSTEP_POST_CHUNKS", kernel.split("+chunks")[1])
+    else:
+        monkeypatch.delenv("FLEETSTEP_POST_CHUNKS", raising=False)
 
     cs = dict(CASES[name])
     E, steps = cs.pop("E"), cs.pop("steps")
