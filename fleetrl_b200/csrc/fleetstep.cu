@@ -998,7 +998,9 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             const bool use_bulk = p.pf_bulk && nb == B && !s_any_reset[it % kPfEnvs] && p.obs != nullptr;
             if (use_bulk) {
                 // the writers have run fence.proxy.async before arriving on bar_done: no second fence here
+#ifndef PF_NOOBS
                 if (lane == 0) bulk_store_s2g_nofence(p.obs + (size_t)e0 * D, obs_tile, (uint32_t)(B * D * 4));
+#endif
             } else if (p.pf_bulk && (D & 3) == 0) {
                 // rows of finishing envs go to terminal_obs: one bulk store per env row (D*4 bytes, 16-byte aligned)
                 if (lane < nb) {
@@ -1187,14 +1189,22 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             const int t1 = min(ev.x + 1, p.T - 1);
             const int4* rp = reinterpret_cast<const int4*>(p.ev_rec + (size_t)t1 * N + n);
             cp_async4_hint(st + kPfStA32 + j * 4, p.actions + i, stream);
+#ifndef PF_NOSTATE
             cp_async8_hint(st + kPfStSoc + j * 8, p.soc + i, stream);
             cp_async4_hint(st + kPfStHl + j * 4, p.hl + i, stream);
             cp_async8_hint(st + kPfStSoh + j * 8, p.soh + i, stream);
+#endif
+#ifndef PF_NOHIST
             cp_async8_hint(st + kPfStSdeg + j * 8,
                            p.hist + ((size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)((p.calc_deg ? k : (k & 1)) * N)), stream);
+#endif
+#ifndef PF_NOREC
             cp_async16_hint(st + kPfStR0 + j * 16, rp, keep);
             cp_async16_hint(st + kPfStR1 + j * 16, rp + 1, keep);
             if (n < H) cp_async4_hint(st + kPfStHv + j * 4, p.hdr + (size_t)t1 * p.hdr_stride + n, keep);
+#else
+            (void)rp;
+#endif
         }
         cp_async_commit();
     };
@@ -1352,9 +1362,13 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
         // stores to wait for, not these
         if (active) {
             const size_t i = (size_t)tile * cstride + j;
+#ifndef PF_NOSTATE
             __stcs(p.soc + i, o_soc);
             __stcs(p.hl + i, o_hl);
+#endif
+#ifndef PF_NOHIST
             __stcs(p.hist + o_hist, o_sdeg);
+#endif
         }
         PF_MARK(6);
         issue_copies(tile + kPfStages * G, ev_next, stg);     // refill the stage this tile has just consumed
