@@ -2730,17 +2730,13 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     if (cap > 32767) return fail(h, FLEET_E_INVALID, "episodes longer than 32765 steps are not supported (15-bit sample indices)");
     size_t smp = post_smem_bytes(cap);
     if (!(c.calc_degradation && c.deg_mode == FLEET_DEG_SEI)) smp = 16;
-    if ((int64_t)smp > (int64_t)h->max_smem_optin) {
-        char buf[256];
-        snprintf(buf, sizeof buf, "post kernel needs %zu bytes of shared memory for the rainflow cycle records of a %d-step episode "
-                 "but the device allows %d; spilling the records to global memory is not implemented yet", smp, c.episode_steps,
-                 h->max_smem_optin);
-        return fail(h, FLEET_E_INVALID, buf);
-    }
+    // the thread-per-vehicle kernel keeps one record per cycle for 64 vehicles in shared memory: too much for very long
+    // episodes, where only the cooperative kernel (which splits the vehicles into chunks) is available
+    const bool v1_ok = (int64_t)smp <= (int64_t)h->max_smem_optin;
     h->smem_post = smp;
     h->num_sms = prop.multiProcessorCount;
     h->need_post = (c.calc_degradation || c.auto_reset) ? 1 : 0;
-    {
+    if (v1_ok) {
         int per_sm = 1;
         CUDA_TRY(h, cudaFuncSetAttribute(pick_post(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp));
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post(h), kPostThreads, smp));
@@ -2748,7 +2744,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
         const int64_t g = (int64_t)h->num_sms * per_sm;
         h->grid_post = (int)(g < E ? g : E);
     }
-    if (c.calc_degradation && c.deg_mode == FLEET_DEG_SEI) {
+    if (v1_ok && c.calc_degradation && c.deg_mode == FLEET_DEG_SEI) {
         int sc = 64;
         while (sc < cap) sc <<= 1;
         p.scratch_cap = sc;
@@ -2794,6 +2790,12 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
             const int64_t max_items = (int64_t)E * p.po_nch;
             h->grid_post2 = (int)(g < max_items ? g : max_items);
             h->use_post2 = 1;
+        }
+        if (!h->use_post2 && !v1_ok && h->need_post) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "a %d-step episode does not fit the post kernels' shared-memory staging (%zu bytes needed, "
+                     "the device allows %d)", c.episode_steps, smp, h->max_smem_optin);
+            return fail(h, FLEET_E_INVALID, buf);
         }
     }
     h->smem_step = sm;

@@ -29,6 +29,9 @@ CASES = {
     "lmd_5ev_soh09": dict(n_evs=5, days=12, use_case="lmd", E=16, steps=120, over=dict(init_soh=0.9)),
     "lmd_4ev_no_autoreset": dict(n_evs=4, days=12, use_case="lmd", E=8, steps=110, over=dict(auto_reset=0)),
     "lmd_12ev_nodeg_exact_soc": dict(n_evs=12, days=12, use_case="lmd", E=64, steps=230, over=dict(calc_degradation=0)),
+    # ten-day episodes: histories of up to 961 rows (the cooperative post kernel splits the vehicles into chunks to fit
+    # its shared-memory staging; ten daily evaluations per episode over a growing history)
+    "lmd_9ev_10day_episodes": dict(n_evs=9, days=30, use_case="lmd", E=3, steps=1000, episode_hours=240),
     # configurations that qualify for the persistent TMA kernel (even N, D % 4 == 0, aligned last tile)
     "lmd_50ev_e36": dict(n_evs=50, days=8, use_case="lmd", E=36, steps=120),
     "ut_10ev_e50": dict(n_evs=10, days=10, use_case="ut", E=50, steps=210, episode_hours=48),
