@@ -556,6 +556,82 @@ __device__ __forceinline__ void bulk_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// ------------------------------------------------------------------------------------------ one (env, EV) slot
+// The reference's inner logic for one vehicle and one step, shared by the three step kernels: EvCharger.charge
+// (ev_charger.py:98-206), the action*there term of check_violation (fleet_environment.py:491), the SOC update
+// (:470) and the departure / stay / gone / arrival transition with the target flip and soc_deg (:528-623).
+// float64, reference operation order, no FMA contraction (the file is compiled with -fmad=false).
+//   in : es (per-env factors of time t: S, F_cr, F_dr, Rfac, pv_share, flags), a = action, soh, sr / ntl = schedule
+//        SOC_on_return / time_left at t+1, there = presence at t, flip = target already raised to 0.9
+//   io : soc, hl, sdeg      out: the vehicle's terms of the five per-env sums
+template <class EnvT>
+__device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es, size_t i, bool flip, double a, double soh,
+                                             double sr, float ntl, int there, double& soc, float& hl, double& sdeg,
+                                             double& q_rew, double& q_cash, double& q_ath, double& q_miss, double& q_nviol) {
+    const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
+    const double cap = soh * p.cap0;                                // episode.battery_cap[car]
+    double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
+    double num = 0;                                                 // next_soc = soc + num / cap
+    if (a >= 0) {                                                   // ev_charger.py:98-156
+        const double dem = (tgt - soc) * cap;
+        const double req = p.P * a * p.dt;
+        if (req * p.eta_c > dem) {
+            const double d = req - dem;
+            const double pen = p.pen_oc * (d * d);
+            c_oc = pen > p.clip_oc ? pen : p.clip_oc;
+        }
+        double en = 0;
+        if (there == 1) en = fmin(dem / p.eta_c, req);              // IEEE divide: SOC must be bit-exact
+        else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
+        num = en * p.eta_c;
+        double ge = en - es.pv_share;
+        ge = ge > 0 ? ge : 0;
+        c_cost = ge * es.S * p.mult;
+        c_cr = es.F_cr * ge;
+    } else if (a < 0) {                                             // ev_charger.py:159-206
+        const double left = -1 * soc * cap;
+        const double req = p.P * a * p.dt;
+        if (req * p.eta_d < left && there != 0) {
+            const double d = left - req;
+            c_oc = p.pen_oc * (d * d);
+        }
+        double en = 0.0;
+        if (there == 1) en = fmax(left, req);
+        else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
+        num = en;
+        c_rev = -1 * en * es.Rfac;
+        c_dr = es.F_dr * en;
+    } else {
+        atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
+    }
+    q_ath = a * (double)there;                                      // fleet_environment.py:491
+    // ev_charger.py:128,189 ; :470.  num == 0 (absent vehicle, zero action) adds exactly 0: skipping the division there
+    // is bit-identical and keeps the warp out of the slow path of the f64 divide.
+    if (num != 0) soc = soc + num / cap;
+
+    // time has advanced to t+1: departure / still there / gone / arrival   :528-618
+    if (hl != 0.f && ntl == 0.f) {
+        const double tg = (p.is_ct && (es.flags & EF_LUNCH)) ? p.target_lunch : tgt;
+        const double diff = tg - soc;
+        if (diff > p.eps) {
+            c_miss = diff; c_nviol = 1;
+            c_dep = -500 / (1 + exp(-16.48461585 * (diff - 0.29229767))) + 1;   // score_config.py:26-30
+        } else {
+            c_dep = p.full_reward;
+        }
+    }
+    if (ntl != 0.f && hl != 0.f) hl -= p.dt_f;
+    else { hl = ntl; soc = sr; }
+    if (soh <= 0.9 && !flip) {                                      // :613-614 (visible from the next step on)
+        p.tflip[i] = 1;
+        atomicAdd(p.n_flips, 1);
+    }
+    if (hl != 0.f) sdeg = soc;                                      // :621-623
+    q_rew = c_cr + c_dr + c_inv + c_oc + c_dep;                     // per-vehicle reward terms (:228,548-590)
+    q_cash = -1 * c_cost + c_rev;                                   // ev_charger.py:225
+    q_miss = c_miss; q_nviol = c_nviol;
+}
+
 // ------------------------------------------------------------------------------------------------ step kernel
 // Work-list entry pushed by the step kernel for envs that need the post kernel (daily degradation and/or reset).
 constexpr int WL_TRIGGER = 1, WL_RESET = 2;
@@ -679,78 +755,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
             double c_rew = 0, c_cash = 0, c_ath = 0, c_miss = 0, c_nviol = 0;
             const bool flip = have_flips && p.tflip[i] != 0;
             if (!(es.flags & EF_FROZEN)) {
-                const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
-                const double cap = soh * p.cap0;                                // episode.battery_cap[car]
-                const int there = rec.there_prev;                               // db.There at t
-                const double a = (double)a32;
-                double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0;
-                double num = 0;                                                 // next_soc = soc + num / cap
-                if (a >= 0) {                                                   // ev_charger.py:98-156
-                    const double dem = (tgt - soc) * cap;
-                    const double req = p.P * a * p.dt;
-                    if (req * p.eta_c > dem) {
-                        const double d = req - dem;
-                        const double pen = p.pen_oc * (d * d);
-                        c_oc = pen > p.clip_oc ? pen : p.clip_oc;
-                    }
-                    double en = 0;
-                    if (there == 1) {
-                        en = fmin(dem / p.eta_c, req);                          // IEEE divide: SOC must be bit-exact
-                    } else if (fabs(a) > 0.05) {
-                        c_inv = p.pen_inv * (a * a);
-                    }
-                    num = en * p.eta_c;
-                    double ge = en - es.pv_share;
-                    ge = ge > 0 ? ge : 0;
-                    c_cost = ge * es.S * p.mult;
-                    c_cr = es.F_cr * ge;
-                } else if (a < 0) {                                             // ev_charger.py:159-206
-                    const double left = -1 * soc * cap;
-                    const double req = p.P * a * p.dt;
-                    if (req * p.eta_d < left && there != 0) {
-                        const double d = left - req;
-                        c_oc = p.pen_oc * (d * d);
-                    }
-                    double en = 0.0;
-                    if (there == 1) en = fmax(left, req);
-                    else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
-                    num = en;
-                    c_rev = -1 * en * es.Rfac;
-                    c_dr = es.F_dr * en;
-                } else {
-                    atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
-                }
-                c_ath = a * (double)there;                                      // fleet_environment.py:491
-                // ev_charger.py:128,189 ; :470.  num == 0 (absent vehicle, zero action) adds exactly 0: skipping the
-                // division there is bit-identical and keeps the warp out of the slow path of the f64 divide.
-                if (num != 0) soc = soc + num / cap;
-
-                // time has advanced to t+1: departure / still there / gone / arrival   :528-618
-                const float ntl = rec.tl;
-                if (hl != 0.f && ntl == 0.f) {
-                    const double tg = (p.is_ct && (es.flags & EF_LUNCH)) ? p.target_lunch : tgt;
-                    const double diff = tg - soc;
-                    if (diff > p.eps) {
-                        c_miss = diff; c_nviol = 1;
-                        c_dep = -500 / (1 + exp(-16.48461585 * (diff - 0.29229767))) + 1;   // score_config.py:26-30
-                    } else {
-                        c_dep = p.full_reward;
-                    }
-                }
-                if (ntl != 0.f && hl != 0.f) hl -= p.dt_f;
-                else { hl = ntl; soc = rec.sr; }
-                if (soh <= 0.9 && !flip) {                                      // :613-614 (visible from the next step on)
-                    p.tflip[i] = 1;
-                    atomicAdd(p.n_flips, 1);
-                }
-                if (hl != 0.f) sdeg = soc;                                      // :621-623
+                ev_slot_step(p, es, i, flip, (double)a32, soh, rec.sr, rec.tl, rec.there_prev, soc, hl, sdeg,
+                             c_rew, c_cash, c_ath, c_miss, c_nviol);
 
                 __stcs(p.soc + i, soc);
                 __stcs(p.hl + i, hl);
                 const size_t hnext = p.calc_deg ? hrow + N : (hrow - (size_t)(k & 1) * N + (size_t)((k + 1) & 1) * N);
                 __stcs(p.hist + hnext, sdeg);                                   // log_soc, :655-656
-                c_rew = c_cr + c_dr + c_inv + c_oc + c_dep;                     // per-vehicle reward terms (:228,548-590)
-                c_cash = -1 * c_cost + c_rev;                                   // ev_charger.py:225
             }
             write_ev_obs<kNorm, kAux>(p, orow, n, soc, hl, rec, flip);
             contrib[Q_REWARD * cstride + j] = c_rew;  contrib[Q_CASH * cstride + j] = c_cash;
@@ -1257,75 +1268,16 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             float hl = reinterpret_cast<const float*>(stp + kPfStHl)[j];
             const double soh = reinterpret_cast<const double*>(stp + kPfStSoh)[j];
             const bool flip = s_have_flips && p.tflip[i] != 0;
-            const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
-            const double cap = soh * p.cap0;                                // episode.battery_cap[car]
-            const int there = rec.there_prev;                               // db.There at t
             const double a = (double)reinterpret_cast<const float*>(stp + kPfStA32)[j];
-            double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
 #ifndef PF_NOMATH
-            double num = 0;
-            if (a >= 0) {                                                   // ev_charger.py:98-156
-                const double dem = (tgt - soc) * cap;
-                const double req = p.P * a * p.dt;
-                if (req * p.eta_c > dem) {
-                    const double d = req - dem;
-                    const double pen = p.pen_oc * (d * d);
-                    c_oc = pen > p.clip_oc ? pen : p.clip_oc;
-                }
-                double en = 0;
-                if (there == 1) en = fmin(dem / p.eta_c, req);              // IEEE divide: SOC must be bit-exact
-                else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
-                num = en * p.eta_c;
-                double ge = en - es.pv_share;
-                ge = ge > 0 ? ge : 0;
-                c_cost = ge * es.S * p.mult;
-                c_cr = es.F_cr * ge;
-            } else if (a < 0) {                                             // ev_charger.py:159-206
-                const double left = -1 * soc * cap;
-                const double req = p.P * a * p.dt;
-                if (req * p.eta_d < left && there != 0) {
-                    const double d = left - req;
-                    c_oc = p.pen_oc * (d * d);
-                }
-                double en = 0.0;
-                if (there == 1) en = fmax(left, req);
-                else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
-                num = en;
-                c_rev = -1 * en * es.Rfac;
-                c_dr = es.F_dr * en;
-            } else {
-                atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
-            }
-            const double c_ath = a * (double)there;                         // fleet_environment.py:491
-            if (num != 0) soc = soc + num / cap;                            // ev_charger.py:128,189
-
-            const float ntl = rec.tl;                                       // departure / stay / gone / arrival :528-618
-            if (hl != 0.f && ntl == 0.f) {
-                const double tg = (p.is_ct && (es.flags & EF_LUNCH)) ? p.target_lunch : tgt;
-                const double diff = tg - soc;
-                if (diff > p.eps) {
-                    c_miss = diff; c_nviol = 1;
-                    c_dep = -500 / (1 + exp(-16.48461585 * (diff - 0.29229767))) + 1;   // score_config.py:26-30
-                } else {
-                    c_dep = p.full_reward;
-                }
-            }
-            if (ntl != 0.f && hl != 0.f) hl -= p.dt_f;
-            else { hl = ntl; soc = rec.sr; }
-            if (soh <= 0.9 && !flip) {                                      // :613-614
-                p.tflip[i] = 1;
-                atomicAdd(p.n_flips, 1);
-            }
+            ev_slot_step(p, es, i, flip, a, soh, rec.sr, rec.tl, rec.there_prev, soc, hl, sdeg,
+                         q_rew, q_cash, q_ath, q_miss, q_nviol);
 #else  /* diagnostic build: same loads and stores, almost no arithmetic */
-            double num = a; soc = soc + a * 1e-3; c_cr = a; c_miss = soh; const double c_ath = a; const float ntl = rec.tl; if (ntl != 0.f) hl = ntl; (void)num; (void)tgt; (void)cap; (void)there;
+            soc = soc + a * 1e-3; q_rew = a; q_miss = soh; q_ath = a; if (rec.tl != 0.f) hl = rec.tl;
+            if (hl != 0.f) sdeg = soc;
 #endif
-            if (hl != 0.f) sdeg = soc;                                      // :621-623
-
             o_soc = soc; o_hl = hl; o_sdeg = sdeg;
             o_hist = (size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)((p.calc_deg ? k + 1 : ((k + 1) & 1)) * N);
-            q_rew = c_cr + c_dr + c_inv + c_oc + c_dep;
-            q_cash = -1 * c_cost + c_rev;
-            q_ath = c_ath; q_miss = c_miss; q_nviol = c_nviol;
             {
                 const int4 r1 = reinterpret_cast<const int4*>(stp + kPfStR1)[j];
                 rec.tt = __int_as_float(r1.x); rec.cl = __int_as_float(r1.y);
@@ -1691,75 +1643,22 @@ __global__ void __launch_bounds__(kWsThreads, 3) fleet_step_tma_kernel(const Ste
         if (active) {
             const size_t i = (size_t)e0 * N + j;
             const bool flip = have_flips && p.tflip[i] != 0;
-            const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
-            const double cap = soh * p.cap0;                                // episode.battery_cap[car]
-            const int there = rec.there_prev;                               // db.There at t
-            const double a = (double)a32;
-            double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
-            double num = 0;
-            if (a >= 0) {                                                   // ev_charger.py:98-156
-                const double dem = (tgt - soc) * cap;
-                const double req = p.P * a * p.dt;
-                if (req * p.eta_c > dem) {
-                    const double d = req - dem;
-                    const double pen = p.pen_oc * (d * d);
-                    c_oc = pen > p.clip_oc ? pen : p.clip_oc;
-                }
-                double en = 0;
-                if (there == 1) en = fmin(dem / p.eta_c, req);              // IEEE divide: SOC must be bit-exact
-                else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
-                num = en * p.eta_c;
-                double ge = en - ePv;
-                ge = ge > 0 ? ge : 0;
-                c_cost = ge * eS * p.mult;
-                c_cr = eFcr * ge;
-            } else if (a < 0) {                                             // ev_charger.py:159-206
-                const double left = -1 * soc * cap;
-                const double req = p.P * a * p.dt;
-                if (req * p.eta_d < left && there != 0) {
-                    const double d = left - req;
-                    c_oc = p.pen_oc * (d * d);
-                }
-                double en = 0.0;
-                if (there == 1) en = fmax(left, req);
-                else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
-                num = en;
-                c_rev = -1 * en * eRfac;
-                c_dr = eFdr * en;
-            } else {
-                atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
-            }
-            const double c_ath = a * (double)there;                         // fleet_environment.py:491
-            if (num != 0) soc = soc + num / cap;                            // ev_charger.py:128,189
-
-            const float ntl = rec.tl;                                       // departure / stay / gone / arrival :528-618
-            if (hl != 0.f && ntl == 0.f) {
-                const double tg = (p.is_ct && (eflags_next & TF_LUNCH)) ? p.target_lunch : tgt;
-                const double diff = tg - soc;
-                if (diff > p.eps) {
-                    c_miss = diff; c_nviol = 1;
-                    c_dep = -500 / (1 + exp(-16.48461585 * (diff - 0.29229767))) + 1;   // score_config.py:26-30
-                } else {
-                    c_dep = p.full_reward;
-                }
-            }
-            if (ntl != 0.f && hl != 0.f) hl -= p.dt_f;
-            else { hl = ntl; soc = rec.sr; }
-            if (soh <= 0.9 && !flip) {                                      // :613-614
-                p.tflip[i] = 1;
-                atomicAdd(p.n_flips, 1);
-            }
-            if (hl != 0.f) sdeg = soc;                                      // :621-623
+            double q_rew = 0, q_cash = 0, q_ath = 0, q_miss = 0, q_nviol = 0;
+            struct { double S, F_cr, F_dr, Rfac, pv_share; int flags; } es;   // per-env factors read from the stage above
+            es.S = eS; es.F_cr = eFcr; es.F_dr = eFdr; es.Rfac = eRfac; es.pv_share = ePv;
+            es.flags = (eflags_next & TF_LUNCH) ? EF_LUNCH : 0;
+            ev_slot_step(p, es, i, flip, (double)a32, soh, rec.sr, rec.tl, rec.there_prev, soc, hl, sdeg,
+                         q_rew, q_cash, q_ath, q_miss, q_nviol);
 
             reinterpret_cast<double*>(so + L.o_soc)[j] = soc;
             reinterpret_cast<float*>(so + L.o_hl)[j] = hl;
             reinterpret_cast<double*>(so + L.o_hist)[j] = sdeg;
             write_ev_obs<kNorm, kAux>(p, obs_tile + b * D, n, soc, hl, rec, flip);
-            contrib[Q_REWARD * cstride + j] = c_cr + c_dr + c_inv + c_oc + c_dep;
-            contrib[Q_CASH * cstride + j] = -1 * c_cost + c_rev;
-            contrib[Q_ATH * cstride + j] = c_ath;
-            contrib[Q_MISS * cstride + j] = c_miss;
-            contrib[Q_NVIOL * cstride + j] = c_nviol;
+            contrib[Q_REWARD * cstride + j] = q_rew;
+            contrib[Q_CASH * cstride + j] = q_cash;
+            contrib[Q_ATH * cstride + j] = q_ath;
+            contrib[Q_MISS * cstride + j] = q_miss;
+            contrib[Q_NVIOL * cstride + j] = q_nviol;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (bulk stores)
         mbar_arrive(&done[ob]);
