@@ -1033,7 +1033,12 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             // ---- per-env sums: one lane per (quantity, env); five interleaved partial sums in car order, combined in
             // a fixed order (deterministic run to run; the dependent-add chain is 5x shorter than a sequential sum)
             if (it >= 2) mbar_wait(&bar_sums_free[sbuf], (uint32_t)(((it >> 1) - 1) & 1));
+#ifdef PF_NOEPI
+            if (lane < kNQ * nb) sums_w[lane] = 0;
+            for (int w = lane; w < 0; w += 32) {
+#else
             for (int w = lane; w < kNQ * nb; w += 32) {
+#endif
                 const int q = w / nb, bb = w - q * nb;
                 const double* c = contrib + q * cslots + bb * cper;
                 double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
@@ -1122,7 +1127,11 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             mbar_wait(&bar_sums_ready[sbuf], (uint32_t)((it >> 1) & 1));   // warp 1 has summed tile `tile`
 
             // ---- env-level finalisation: one lane per env
+#ifdef PF_NOEPI
+            for (int bb = lane; bb < 0; bb += 32) {
+#else
             for (int bb = lane; bb < nb; bb += 32) {
+#endif
                 const int e = e0 + bb;
                 const PfEnv& es = envs[bb];
                 double* stt = p.stats + (size_t)(tile % kStatStripes) * FLEET_S__COUNT;
