@@ -92,6 +92,7 @@ FIELDS = {
     "ep_return": (12, np.float64, False), "ep_count": (13, np.int32, False),
     "last_ep_return": (14, np.float64, False), "n_cycles": (15, np.int32, True),
     "last_deg": (16, np.float64, True), "overload": (17, np.float64, False), "soc_viol": (18, np.float64, False),
+    "charge_log": (19, np.float64, True),        # only after FleetStepHandle.enable_charge_log()
 }
 
 # FLEET_S_*

@@ -21,7 +21,7 @@ EXPORTS = [
     "fleet_abi_version", "fleet_create", "fleet_destroy", "fleet_obs_dim", "fleet_num_evs", "fleet_num_envs",
     "fleet_reset", "fleet_step", "fleet_step_host", "fleet_set_next_start", "fleet_get_state", "fleet_set_state",
     "fleet_field_info", "fleet_get_stats", "fleet_reset_stats", "fleet_check_errors", "fleet_launch_count",
-    "fleet_device_bytes", "fleet_last_error", "fleet_set_timing", "fleet_get_timing", "fleet_step_kernel_name", "fleet_policy_actions", "fleet_policy_reset",
+    "fleet_device_bytes", "fleet_last_error", "fleet_set_timing", "fleet_get_timing", "fleet_step_kernel_name", "fleet_policy_actions", "fleet_policy_reset", "fleet_enable_charge_log",
 ]
 
 
@@ -61,6 +61,7 @@ def load_library(path: str = LIB_PATH):
     L.fleet_device_bytes.restype = i64
     L.fleet_policy_actions.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.fleet_policy_reset.argtypes = [vp, vp]
+    L.fleet_enable_charge_log.argtypes = [vp, i32]
     L.fleet_step_kernel_name.argtypes = [vp]
     L.fleet_step_kernel_name.restype = C.c_char_p
     L.fleet_set_timing.argtypes = [vp, i32]
@@ -214,6 +215,10 @@ class FleetStepHandle:
 
     def policy_reset(self):
         self._check(self.lib.fleet_policy_reset(self._h, _stream_ptr(self.device)), "fleet_policy_reset")
+
+    def enable_charge_log(self, enable=True):
+        """Keep EvCharger's per-vehicle charge_log of every step (field "charge_log"); off by default."""
+        self._check(self.lib.fleet_enable_charge_log(self._h, 1 if enable else 0), "fleet_enable_charge_log")
 
     def set_timing(self, enable=True):
         self._check(self.lib.fleet_set_timing(self._h, 1 if enable else 0), "fleet_set_timing")

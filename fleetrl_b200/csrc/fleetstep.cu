@@ -121,6 +121,7 @@ struct StepParams {
     double* life;             // [E][N]
     int* n_cycles;            // [E][N]
     double* last_deg;         // [E][N]
+    double* charge_log;       // [E][N] or nullptr: energy into (+) / out of (-) each battery in the last step
     double* stats;            // [kStatStripes][FLEET_S__COUNT]
     unsigned int* err_flags;  // [1]
     const int* next_start;    // [E] or nullptr
@@ -567,7 +568,8 @@ __device__ __forceinline__ void bulk_store_wait_read() {
 template <class EnvT>
 __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es, size_t i, bool flip, double a, double soh,
                                              double sr, float ntl, int there, double& soc, float& hl, double& sdeg,
-                                             double& q_rew, double& q_cash, double& q_ath, double& q_miss, double& q_nviol) {
+                                             double& q_rew, double& q_cash, double& q_ath, double& q_miss, double& q_nviol,
+                                             double& q_en) {
     const double tgt = flip ? 0.9 : p.target;                       // FleetEnv.target_soc[car]
     const double cap = soh * p.cap0;                                // episode.battery_cap[car]
     double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
@@ -584,6 +586,7 @@ __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es
         if (there == 1) en = fmin(dem / p.eta_c, req);              // IEEE divide: SOC must be bit-exact
         else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
         num = en * p.eta_c;
+        q_en = en;                                                  // charge_log, ev_charger.py:212
         double ge = en - es.pv_share;
         ge = ge > 0 ? ge : 0;
         c_cost = ge * es.S * p.mult;
@@ -599,9 +602,11 @@ __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es
         if (there == 1) en = fmax(left, req);
         else if (fabs(a) > 0.05) c_inv = p.pen_inv * (a * a);
         num = en;
+        q_en = en;
         c_rev = -1 * en * es.Rfac;
         c_dr = es.F_dr * en;
     } else {
+        q_en = 0;
         atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
     }
     q_ath = a * (double)there;                                      // fleet_environment.py:491
@@ -755,13 +760,17 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
             double c_rew = 0, c_cash = 0, c_ath = 0, c_miss = 0, c_nviol = 0;
             const bool flip = have_flips && p.tflip[i] != 0;
             if (!(es.flags & EF_FROZEN)) {
+                double c_en = 0;
                 ev_slot_step(p, es, i, flip, (double)a32, soh, rec.sr, rec.tl, rec.there_prev, soc, hl, sdeg,
-                             c_rew, c_cash, c_ath, c_miss, c_nviol);
+                             c_rew, c_cash, c_ath, c_miss, c_nviol, c_en);
+                if (p.charge_log) p.charge_log[i] = c_en;
 
                 __stcs(p.soc + i, soc);
                 __stcs(p.hl + i, hl);
                 const size_t hnext = p.calc_deg ? hrow + N : (hrow - (size_t)(k & 1) * N + (size_t)((k + 1) & 1) * N);
                 __stcs(p.hist + hnext, sdeg);                                   // log_soc, :655-656
+            } else if (p.charge_log) {
+                p.charge_log[i] = 0;                                            // frozen env: nothing flows
             }
             write_ev_obs<kNorm, kAux>(p, orow, n, soc, hl, rec, flip);
             contrib[Q_REWARD * cstride + j] = c_rew;  contrib[Q_CASH * cstride + j] = c_cash;
@@ -1258,7 +1267,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
         PF_MARK(2);
 
         double q_rew = 0, q_cash = 0, q_ath = 0, q_miss = 0, q_nviol = 0;   // this vehicle's terms of the per-env sums
-        double o_soc = 0, o_sdeg = 0;                                       // new state, stored after the hand-off
+        double o_soc = 0, o_sdeg = 0, o_en = 0;                             // new state, stored after the hand-off
         float o_hl = 0.f;
         size_t o_hist = 0;
         if (active) {
@@ -1280,7 +1289,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             const double a = (double)reinterpret_cast<const float*>(stp + kPfStA32)[j];
 #ifndef PF_NOMATH
             ev_slot_step(p, es, i, flip, a, soh, rec.sr, rec.tl, rec.there_prev, soc, hl, sdeg,
-                         q_rew, q_cash, q_ath, q_miss, q_nviol);
+                         q_rew, q_cash, q_ath, q_miss, q_nviol, o_en);
 #else  /* diagnostic build: same loads and stores, almost no arithmetic */
             soc = soc + a * 1e-3; q_rew = a; q_miss = soh; q_ath = a; if (rec.tl != 0.f) hl = rec.tl;
             if (hl != 0.f) sdeg = soc;
@@ -1330,6 +1339,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
 #ifndef PF_NOHIST
             __stcs(p.hist + o_hist, o_sdeg);
 #endif
+            if (p.charge_log) __stcs(p.charge_log + i, o_en);
         }
         PF_MARK(6);
         issue_copies(tile + kPfStages * G, ev_next, stg);     // refill the stage this tile has just consumed
@@ -1656,8 +1666,10 @@ __global__ void __launch_bounds__(kWsThreads, 3) fleet_step_tma_kernel(const Ste
             struct { double S, F_cr, F_dr, Rfac, pv_share; int flags; } es;   // per-env factors read from the stage above
             es.S = eS; es.F_cr = eFcr; es.F_dr = eFdr; es.Rfac = eRfac; es.pv_share = ePv;
             es.flags = (eflags_next & TF_LUNCH) ? EF_LUNCH : 0;
+            double q_en = 0;
             ev_slot_step(p, es, i, flip, (double)a32, soh, rec.sr, rec.tl, rec.there_prev, soc, hl, sdeg,
-                         q_rew, q_cash, q_ath, q_miss, q_nviol);
+                         q_rew, q_cash, q_ath, q_miss, q_nviol, q_en);
+            if (p.charge_log) p.charge_log[i] = q_en;
 
             reinterpret_cast<double*>(so + L.o_soc)[j] = soc;
             reinterpret_cast<float*>(so + L.o_hl)[j] = hl;
@@ -2244,6 +2256,7 @@ struct FleetHandle {
     int use_post2 = 0, grid_post2 = 0;
     size_t smem_post2 = 0;
     int max_smem_optin = 0;
+    double* charge_log_buf = nullptr;   // fleet_enable_charge_log
     // rule-based policies (fleet_policy_actions): minute of day per table row; night-charging state, double buffered
     uint16_t* tod = nullptr;
     int2* pol_state[2] = {nullptr, nullptr};
@@ -2353,6 +2366,17 @@ int fleet_obs_dim(const FleetHandle* h) { return h ? h->D : FLEET_E_INVALID; }
 int fleet_num_evs(const FleetHandle* h) { return h ? h->N : FLEET_E_INVALID; }
 int fleet_num_envs(const FleetHandle* h) { return h ? h->E : FLEET_E_INVALID; }
 int64_t fleet_launch_count(const FleetHandle* h) { return h ? h->launches : 0; }
+
+int fleet_enable_charge_log(FleetHandle* h, int32_t enable) {
+    if (!h) return FLEET_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (enable && !h->charge_log_buf) {
+        int rc;
+        if ((rc = dev_alloc(h, &h->charge_log_buf, (size_t)h->E * h->N))) return rc;
+    }
+    h->p.charge_log = enable ? h->charge_log_buf : nullptr;
+    return FLEET_OK;
+}
 
 const char* fleet_step_kernel_name(const FleetHandle* h) {
     if (!h) return "";
@@ -2890,7 +2914,7 @@ int fleet_field_info(const FleetHandle* h, int32_t field, int32_t* elem_bytes, i
     int eb = 8; int64_t cnt = EN;
     switch (field) {
         case FLEET_F_SOC: case FLEET_F_SOC_DEG: case FLEET_F_SOH: case FLEET_F_TARGET_SOC: case FLEET_F_FD_CYC:
-        case FLEET_F_LIFE: case FLEET_F_LAST_DEG: eb = 8; cnt = EN; break;
+        case FLEET_F_LIFE: case FLEET_F_LAST_DEG: case FLEET_F_CHARGE_LOG: eb = 8; cnt = EN; break;
         case FLEET_F_HOURS_LEFT: eb = 4; cnt = EN; break;
         case FLEET_F_RF_LEN: case FLEET_F_N_CYCLES: eb = 4; cnt = EN; break;
         case FLEET_F_TIME_IDX: case FLEET_F_FINISH_IDX: case FLEET_F_EP_COUNT: eb = 4; cnt = E; break;
@@ -2916,6 +2940,7 @@ static const void* plain_field_ptr(const FleetHandle* h, int32_t field) {
         case FLEET_F_LAST_EP_RETURN: return p.env_f64 + (size_t)EF_LAST_EP_RETURN * h->E;
         case FLEET_F_N_CYCLES: return p.n_cycles;
         case FLEET_F_LAST_DEG: return p.last_deg;
+        case FLEET_F_CHARGE_LOG: return p.charge_log;
         case FLEET_F_OVERLOAD: return p.env_f64 + (size_t)EF_OVERLOAD * h->E;
         case FLEET_F_SOC_VIOL: return p.env_f64 + (size_t)EF_SOC_VIOL * h->E;
         default: return nullptr;
@@ -2927,6 +2952,8 @@ int fleet_get_state(FleetHandle* h, int32_t field, void* dst_dev, void* stream) 
     int32_t eb; int64_t cnt;
     if (fleet_field_info(h, field, &eb, &cnt)) return fail(h, FLEET_E_INVALID, "unknown field");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    if (field == FLEET_F_CHARGE_LOG && !h->p.charge_log)
+        return fail(h, FLEET_E_STATE, "FLEET_F_CHARGE_LOG is only kept after fleet_enable_charge_log(h, 1)");
     const void* src = plain_field_ptr(h, field);
     if (src) {
         CUDA_TRY(h, cudaMemcpyAsync(dst_dev, src, (size_t)cnt * eb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));

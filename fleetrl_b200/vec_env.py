@@ -167,8 +167,8 @@ class FleetVecEnv:
     def enable_log(self, indices=(0,)):
         """Record the reference's per-step log rows for the given envs (evaluation runs: a handful of envs; every
         logged step reads state back from the device).  Rows follow fleet_environment.py:420-432 (reset row) and
-        :679-690 (one row per step that does not end the episode).  "Charging energy" (EvCharger's charge_log) is not
-        kept by the kernels and is logged as NaN."""
+        :679-690 (one row per step that does not end the episode)."""
+        self.handle.enable_charge_log(True)          # "Charging energy" = EvCharger's charge_log (ev_charger.py:212)
         self._log_idx = [int(i) for i in self._indices(indices)]
         self._log_rows = {i: [] for i in self._log_idx}
         self._log_reset_rows(self._log_idx)
@@ -195,6 +195,7 @@ class FleetVecEnv:
         rew, cash = h.get("reward64").cpu().numpy(), h.get("cashflow").cpu().numpy()
         ovl, viol = h.get("overload").cpu().numpy(), h.get("soc_viol").cpu().numpy()
         soh, deg = h.get("soh").cpu().numpy(), h.get("last_deg").cpu().numpy()
+        clog = h.get("charge_log").cpu().numpy()
         obs = self._obs.cpu().numpy()
         act = actions.detach().cpu().numpy() if torch.is_tensor(actions) else np.asarray(actions)
         act = act.reshape(self.num_envs, self.num_cars)
@@ -211,7 +212,7 @@ class FleetVecEnv:
                          "Reward": float(rew[i]), "Cashflow": float(cash[i]), "Penalties": float(rew[i] - cash[i] * pm),
                          "Grid overloading": float(ovl[i]), "SOC violation": float(viol[i]),
                          "Degradation": deg[i].copy() if trig else 0.0,
-                         "Charging energy": np.full(self.num_cars, np.nan), "SOH": soh[i].copy()})
+                         "Charging energy": clog[i].copy(), "SOH": soh[i].copy()})
         self._log_reset_rows([i for i in idx if done[i]])
 
     def baseline_actions(self, policy, out=None):

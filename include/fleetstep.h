@@ -124,7 +124,9 @@ enum {
     FLEET_F_LAST_DEG = 16,   /* double [E][N]  degradation returned by the last daily evaluation               */
     FLEET_F_OVERLOAD = 17,   /* double [E]     grid overload kW of the last step  load_calculation.py:93       */
     FLEET_F_SOC_VIOL = 18,   /* double [E]     cum_soc_missing of the last step   fleet_environment.py:544,661 */
-    FLEET_F__COUNT = 19
+    FLEET_F_CHARGE_LOG = 19, /* double [E][N]  EvCharger's charge_log of the last step (kWh into (+) / out of (-) each battery),
+                              *                 ev_charger.py:212; only kept after fleet_enable_charge_log(h, 1)           */
+    FLEET_F__COUNT = 20
 };
 
 /* Episode statistics (sums over all envs of the handle since the last fleet_reset_stats); the columns of the
@@ -235,6 +237,11 @@ enum { FLEET_POLICY_UNCONTROLLED = 0, FLEET_POLICY_DISTRIBUTED = 1, FLEET_POLICY
 int fleet_policy_actions(FleetHandle* h, int32_t policy, int32_t charging_hour, int32_t charging_minute, int32_t max_hours,
                          float* actions_dev, void* stream);
 int fleet_policy_reset(FleetHandle* h, void* stream);
+
+/* Keep EvCharger.charge's per-vehicle charge_log (ev_charger.py:80,212; the "Charging energy" column of
+ * DataLogger.log_data) of every step in device memory, readable as FLEET_F_CHARGE_LOG.  Off by default: it costs
+ * 8 bytes of HBM writes per EV-step. */
+int fleet_enable_charge_log(FleetHandle* h, int32_t enable);
 
 const char* fleet_step_kernel_name(const FleetHandle* h);   /* which step kernel fleet_create selected */
 int fleet_set_timing(FleetHandle* h, int32_t enable);

@@ -45,6 +45,7 @@ typedef struct OracleEnv {
     double *soc, *hl, *soc_deg, *soh, *cap, *target;      /* [N] */
     double *rf_len, *fd_cyc, *life, *sei_soh;             /* [N] RainflowSeiDegradation members           */
     double *last_deg;                                      /* [N]                                          */
+    double *charge_log;                                    /* [N] EvCharger's charge_log of the last step, ev_charger.py:212 */
     int32_t *n_cycles;                                     /* [N] len(rainflow_result) at last evaluation  */
     double *hist;                                          /* [hist_cap][N] LogDataDeg.soc_log             */
     int32_t hist_len, hist_cap;
@@ -407,6 +408,7 @@ static void env_step(Oracle* o, OracleEnv* e, const float* act, float* obs, Step
                 if (fabs(a) > 0.05) invalid_action_penalty += c->penalty_invalid_action * (a * a);  /* :120-122 */
             }
             next_soc[n] = e->soc[n] + energy * c->charging_eff / e->cap[n];                    /* :128 */
+            e->charge_log[n] = energy;                                                         /* :212 */
             double pv_energy = tb->pv ? tb->pv[t] * dt : 0.0;                                  /* :133-136 */
             double grid_energy = energy - (pv_energy / connected);                             /* :142 */
             grid_energy = grid_energy > 0 ? grid_energy : 0;
@@ -427,11 +429,13 @@ static void env_step(Oracle* o, OracleEnv* e, const float* act, float* obs, Step
                 if (fabs(a) > 0.05) invalid_action_penalty += c->penalty_invalid_action * (a * a);  /* :180-182 */
             }
             next_soc[n] = e->soc[n] + energy / e->cap[n];                                      /* :189 */
+            e->charge_log[n] = energy;                                                         /* :212 */
             discharging_revenue += (-1 * energy * c->discharging_eff * tb->tariff[t] / 1000
                                     * (1 - c->feed_in_deduction));                             /* :196-199 */
             discharging_reward += (-1 * c->price_multiplier * tb->tariff_reward_curve[t] / 1000 * energy); /* :204-206 */
         } else {
             next_soc[n] = e->soc[n];   /* NaN action: the reference raises; flagged above */
+            e->charge_log[n] = 0;
         }
     }
     double cashflow = -1 * charging_cost + discharging_revenue;                                /* :225 */
@@ -522,10 +526,10 @@ Oracle* oracle_create(const FleetConsts* consts, const FleetTables* tb, int32_t 
     o->envs = (OracleEnv*)calloc((size_t)E, sizeof(OracleEnv));
     for (int32_t i = 0; i < E; i++) {
         OracleEnv* e = &o->envs[i];
-        double* blk = (double*)calloc(11 * N, sizeof(double));
+        double* blk = (double*)calloc(12 * N, sizeof(double));
         e->soc = blk; e->hl = blk + N; e->soc_deg = blk + 2 * N; e->soh = blk + 3 * N; e->cap = blk + 4 * N;
         e->target = blk + 5 * N; e->rf_len = blk + 6 * N; e->fd_cyc = blk + 7 * N; e->life = blk + 8 * N;
-        e->sei_soh = blk + 9 * N; e->last_deg = blk + 10 * N;
+        e->sei_soh = blk + 9 * N; e->last_deg = blk + 10 * N; e->charge_log = blk + 11 * N;
         e->n_cycles = (int32_t*)calloc(N, sizeof(int32_t));
         for (size_t n = 0; n < N; n++) {
             e->target[n] = 1.0 * consts->target_soc;                    /* fleet_environment.py:263 */
@@ -590,6 +594,7 @@ static void* step_range(void* arg) {
             if (j->cashflow) j->cashflow[i] = 0;
             if (j->done) j->done[i] = 1;
             e->last_reward = 0; e->last_cashflow = 0; e->last_overload = 0; e->last_soc_viol = 0;
+            memset(e->charge_log, 0, sizeof(double) * N);
             continue;
         }
         double* target_before = scratch + N;      /* aux block uses the targets as of the observer call (:511) */
@@ -676,6 +681,7 @@ int32_t oracle_get_state(const Oracle* o, int32_t field, void* dst) {
             case FLEET_F_LAST_EP_RETURN: ((double*)dst)[i] = e->last_ep_return; break;
             case FLEET_F_N_CYCLES: memcpy((int32_t*)dst + (size_t)i * N, e->n_cycles, 4 * (size_t)N); break;
             case FLEET_F_LAST_DEG: memcpy((double*)dst + (size_t)i * N, e->last_deg, 8 * (size_t)N); break;
+            case FLEET_F_CHARGE_LOG: memcpy((double*)dst + (size_t)i * N, e->charge_log, 8 * (size_t)N); break;
             case FLEET_F_OVERLOAD: ((double*)dst)[i] = e->last_overload; break;
             case FLEET_F_SOC_VIOL: ((double*)dst)[i] = e->last_soc_viol; break;
             default: return -1;

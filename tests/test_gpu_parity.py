@@ -92,6 +92,7 @@ def test_gpu_vs_oracle(name, kernel, monkeypatch):
     rew = torch.zeros(E, dtype=torch.float32, device=dev)
     done = torch.zeros(E, dtype=torch.uint8, device=dev)
 
+    gpu.enable_charge_log(True)              # EvCharger's charge_log of every step (FLEET_F_CHARGE_LOG)
     o_obs = orc.reset()                      # start indices from the counter RNG on both sides
     gpu.reset(obs=obs)
     np.testing.assert_array_equal(gpu.get("time_idx").cpu().numpy(), orc.get("time_idx"))
@@ -123,6 +124,11 @@ def test_gpu_vs_oracle(name, kernel, monkeypatch):
             else:
                 np.testing.assert_allclose(g_v, o_v, rtol=0, atol=1e-12, err_msg=f"{k} step {s}")
                 assert (g_v != o_v).mean() < 1e-2, f"{k} step {s}: too many non-identical elements"
+        g_cl, o_cl = gpu.get("charge_log").cpu().numpy(), orc.get("charge_log")
+        if soc_exact:
+            np.testing.assert_array_equal(g_cl, o_cl, err_msg=f"charge_log step {s}")
+        else:
+            np.testing.assert_allclose(g_cl, o_cl, rtol=0, atol=1e-10, err_msg=f"charge_log step {s}")
         np.testing.assert_allclose(gpu.get("reward64").cpu().numpy(), o_rew, rtol=1e-11, atol=1e-10, err_msg=f"reward step {s}")
         np.testing.assert_allclose(gpu.get("cashflow").cpu().numpy(), o_cash, rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(rew.cpu().numpy(), o_rew.astype(np.float32), rtol=1e-6, atol=1e-6)

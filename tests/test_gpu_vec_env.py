@@ -121,4 +121,6 @@ def test_evaluation_log_columns_and_values():
         assert len(log) == len(steps) + 2                 # the initial reset row and the one after the auto-reset
         assert log["Episode"].iloc[0] == 1 and log["Episode"].iloc[-1] == 2
         assert any(np.ndim(d) == 1 for d in log["Degradation"])   # the 14:45 row carries the per-vehicle degradation
+        ce = np.stack(list(steps["Charging energy"]))
+        assert np.isfinite(ce).all() and (ce != 0).any()          # EvCharger's charge_log per vehicle (kWh)
     env.close()
