@@ -1330,7 +1330,11 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
         PF_MARK(5);
         // the new state goes to HBM after the hand-off: the fence above (MEMBAR + proxy fence) then only has shared-memory
         // stores to wait for, not these
+#ifdef PF_NOSTG
+        if (false) {
+#else
         if (active) {
+#endif
             const size_t i = (size_t)tile * cstride + j;
 #ifndef PF_NOSTATE
             __stcs(p.soc + i, o_soc);
