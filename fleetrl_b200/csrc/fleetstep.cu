@@ -960,7 +960,9 @@ __device__ unsigned long long g_pf_clk[16];
 #define PF_DECL() do {} while (0)
 #define PF_FLUSH(base) do {} while (0)
 #endif
-template <bool kNorm, bool kAux>
+// kLog: keep EvCharger's charge_log (fleet_enable_charge_log); a template flag so that the default instance carries
+// neither the extra live register nor the store.
+template <bool kNorm, bool kAux, bool kLog>
 __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N, B = p.pf_B, D = p.D;
@@ -1343,7 +1345,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
 #ifndef PF_NOHIST
             __stcs(p.hist + o_hist, o_sdeg);
 #endif
-            if (p.charge_log) __stcs(p.charge_log + i, o_en);
+            if (kLog) __stcs(p.charge_log + i, o_en);
         }
         PF_MARK(6);
         issue_copies(tile + kPfStages * G, ev_next, stg);     // refill the stage this tile has just consumed
@@ -2333,9 +2335,13 @@ StepKernel pick_step(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_step_kernel<true, true> : fleet_step_kernel<true, false>;
     return h->c.aux ? fleet_step_kernel<false, true> : fleet_step_kernel<false, false>;
 }
-StepKernel pick_pf(const FleetHandle* h) {
-    if (h->c.normalize) return h->c.aux ? fleet_step_pf_kernel<true, true> : fleet_step_pf_kernel<true, false>;
-    return h->c.aux ? fleet_step_pf_kernel<false, true> : fleet_step_pf_kernel<false, false>;
+StepKernel pick_pf(const FleetHandle* h, bool log) {
+    if (log) {
+        if (h->c.normalize) return h->c.aux ? fleet_step_pf_kernel<true, true, true> : fleet_step_pf_kernel<true, false, true>;
+        return h->c.aux ? fleet_step_pf_kernel<false, true, true> : fleet_step_pf_kernel<false, false, true>;
+    }
+    if (h->c.normalize) return h->c.aux ? fleet_step_pf_kernel<true, true, false> : fleet_step_pf_kernel<true, false, false>;
+    return h->c.aux ? fleet_step_pf_kernel<false, true, false> : fleet_step_pf_kernel<false, false, false>;
 }
 StepKernel pick_tma(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_step_tma_kernel<true, true> : fleet_step_tma_kernel<true, false>;
@@ -2744,8 +2750,9 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
             const size_t smpf = pf_smem_bytes(pfB, N, h->D);
             int per_sm = 0;
             if ((int64_t)smpf <= (int64_t)h->max_smem_optin &&
-                cudaFuncSetAttribute(pick_pf(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smpf) == cudaSuccess &&
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_pf(h), kPfThreads, smpf) == cudaSuccess && per_sm >= 1) {
+                cudaFuncSetAttribute(pick_pf(h, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smpf) == cudaSuccess &&
+                cudaFuncSetAttribute(pick_pf(h, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smpf) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_pf(h, true), kPfThreads, smpf) == cudaSuccess && per_sm >= 1) {
                 h->smem_pf = smpf;
                 const int ntiles = (E + pfB - 1) / pfB;
                 p.pf_B = pfB;
@@ -2838,7 +2845,7 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     if (h->timing && !h->tev.empty()) tev = &h->tev[(size_t)(h->tcount % kTimingRing) * 3];
     if (tev) cudaEventRecord(tev[0], (cudaStream_t)stream);
     if (h->use_tma) fleet_launch_tma(h, p, (cudaStream_t)stream);
-    else if (h->use_pf) pick_pf(h)<<<h->grid_pf, kPfThreads, h->smem_pf, (cudaStream_t)stream>>>(p);
+    else if (h->use_pf) pick_pf(h, p.charge_log != nullptr)<<<h->grid_pf, kPfThreads, h->smem_pf, (cudaStream_t)stream>>>(p);
     else pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
     h->launches++;
     if (tev) cudaEventRecord(tev[1], (cudaStream_t)stream);
