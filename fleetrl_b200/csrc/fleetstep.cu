@@ -2263,6 +2263,7 @@ struct FleetHandle {
     size_t smem_post2 = 0;
     int max_smem_optin = 0;
     double* charge_log_buf = nullptr;   // fleet_enable_charge_log
+    int host_zerocopy = 1;              // fleet_step_host: use page-locked host buffers in place (FLEETSTEP_HOST_ZEROCOPY)
     // rule-based policies (fleet_policy_actions): minute of day per table row; night-charging state, double buffered
     uint16_t* tod = nullptr;
     int2* pol_state[2] = {nullptr, nullptr};
@@ -2741,6 +2742,10 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
         }
     }
     h->smem_step = sm;
+    {
+        const char* zc = getenv("FLEETSTEP_HOST_ZEROCOPY");
+        h->host_zerocopy = (zc && atoi(zc) == 0) ? 0 : 1;
+    }
     // persistent prefetching kernel (default where applicable)
     {
         const char* force = getenv("FLEETSTEP_KERNEL");   // "generic" / "pf" / "tma"; default: pf when applicable
@@ -2874,9 +2879,25 @@ int fleet_step_host(FleetHandle* h, const float* actions_host, float* obs_host, 
         if ((rc = dev_alloc(h, &h->h_reward_dev, (size_t)h->E, false))) return rc;
         if ((rc = dev_alloc(h, &h->h_done_dev, (size_t)h->E, false))) return rc;
     }
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_actions_dev, actions_host, EN * 4, cudaMemcpyHostToDevice, s));
-    if ((rc = fleet_step(h, h->h_actions_dev, h->h_obs_dev, h->h_reward_dev, h->h_done_dev, terminal_obs_dev, stream))) return rc;
-    if (obs_host) CUDA_TRY(h, cudaMemcpyAsync(obs_host, h->h_obs_dev, ED * 4, cudaMemcpyDeviceToHost, s));
+    // Page-locked (pinned / registered) host buffers are device-accessible: the kernels then read the actions and write
+    // the observations straight through PCIe (both directions at once, overlapped with the step itself) instead of
+    // staging them with separate copies.  Pageable buffers take the staging path.  FLEETSTEP_HOST_ZEROCOPY=0 disables.
+    auto mapped = [&](const void* host) -> void* {
+        if (!host || !h->host_zerocopy) return nullptr;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return (at.type == cudaMemoryTypeHost) ? at.devicePointer : nullptr;
+    };
+    const float* a_dev = reinterpret_cast<const float*>(mapped(actions_host));
+    float* o_dev = reinterpret_cast<float*>(mapped(obs_host));
+    if (!a_dev) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_actions_dev, actions_host, EN * 4, cudaMemcpyHostToDevice, s));
+        a_dev = h->h_actions_dev;
+    }
+    const bool obs_direct = (o_dev != nullptr);
+    if (!obs_direct) o_dev = obs_host ? h->h_obs_dev : nullptr;
+    if ((rc = fleet_step(h, a_dev, o_dev, h->h_reward_dev, h->h_done_dev, terminal_obs_dev, stream))) return rc;
+    if (obs_host && !obs_direct) CUDA_TRY(h, cudaMemcpyAsync(obs_host, h->h_obs_dev, ED * 4, cudaMemcpyDeviceToHost, s));
     if (reward_host) CUDA_TRY(h, cudaMemcpyAsync(reward_host, h->h_reward_dev, (size_t)h->E * 4, cudaMemcpyDeviceToHost, s));
     if (done_host) CUDA_TRY(h, cudaMemcpyAsync(done_host, h->h_done_dev, (size_t)h->E, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));

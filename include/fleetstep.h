@@ -191,6 +191,8 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
 
 /* Same step with HOST buffers (pinned or pageable): copies actions up, steps, copies obs/reward/done back and
  * synchronises the stream.  This is the call an SB3-style NumPy caller makes; bench.py times it as "e2e".
+ * Page-locked buffers are used in place: the kernels read the actions and write the observations through PCIe
+ * themselves (both directions at once, overlapped with the step), pageable ones go through staging copies.
  * terminal_obs_dev (optional, DEVICE float32 [E][D]) receives the terminal rows of finished envs as in fleet_step;
  * the caller fetches only the rows it needs (finished envs are rare). */
 int fleet_step_host(FleetHandle* h, const float* actions_host, float* obs_host, float* reward_host,
