@@ -124,3 +124,35 @@ def test_evaluation_log_columns_and_values():
         ce = np.stack(list(steps["Charging energy"]))
         assert np.isfinite(ce).all() and (ce != 0).any()          # EvCharger's charge_log per vehicle (kWh)
     env.close()
+
+
+def test_step_host_pageable_and_pinned_agree():
+    """fleet_step_host with pageable NumPy buffers (staging copies) and with page-locked ones (used in place by the
+    kernels) gives the same outputs as the device-buffer call."""
+    from fleetrl_b200._lib import FleetStepHandle
+    cfg = default_config("lmd", time_picker="random", end_cutoff=10)
+    built = build_fleet(cfg, _inputs(), auto_reset=True)
+    E, N = 40, 6
+    hs = [FleetStepHandle(built.consts, built.tables, E, device=0, env_id_offset=3) for _ in range(3)]
+    D = hs[0].D
+    dev = hs[0].device
+    obs_d = torch.zeros((E, D), dtype=torch.float32, device=dev)
+    rew_d = torch.zeros(E, dtype=torch.float32, device=dev); done_d = torch.zeros(E, dtype=torch.uint8, device=dev)
+    for h in hs:
+        h.reset()
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    o_pin, r_pin, d_pin, a_pin = pin((E, D), torch.float32), pin(E, torch.float32), pin(E, torch.uint8), pin((E, N), torch.float32)
+    o_pg, r_pg, d_pg = np.empty((E, D), np.float32), np.empty(E, np.float32), np.empty(E, np.uint8)
+    rng = np.random.default_rng(5)
+    for s in range(110):
+        a = rng.uniform(-1, 1, (E, N)).astype(np.float32)
+        hs[0].step(torch.from_numpy(a).to(dev), obs_d, rew_d, done_d)
+        hs[1].step_host(a, o_pg, r_pg, d_pg)                    # pageable
+        a_pin[...] = a
+        hs[2].step_host(a_pin, o_pin, r_pin, d_pin)             # page-locked, in place
+        for o, r, d in ((o_pg, r_pg, d_pg), (o_pin, r_pin, d_pin)):
+            np.testing.assert_array_equal(o, obs_d.cpu().numpy(), err_msg=f"step {s}")
+            np.testing.assert_array_equal(r, rew_d.cpu().numpy())
+            np.testing.assert_array_equal(d, done_d.cpu().numpy())
+    for h in hs:
+        h.close()
