@@ -549,8 +549,16 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_store_s2g_nofence(void* gdst, const void* ssrc, uint32_t bytes) {
+#ifndef PF_OBS_DEFAULT_POLICY
+    // observations are written once and never read by the kernels: evict-first keeps them from displacing the tables in L2
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+#endif
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_store_wait_read() {
