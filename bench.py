@@ -34,23 +34,52 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+# BASELINE.json configs[1..4].  cfg2 is the metric's configuration; the others are selected with --config.
+CONFIGS = {
+    "cfg2": dict(use_case="lmd", evs=50, envs=65536, episode_hours=24, minutes=15, over={},
+                 label="LMD fleet, 50 EVs, rainflow-SEI degradation, 15-min steps, 24 h episodes, full observer (cfg2)"),
+    "cfg3": dict(use_case="ct", evs=20, envs=65536, episode_hours=48, minutes=15, over={},
+                 label="caretaker fleet, 20 EVs, building load + PV + grid cap, lunch-break target, rainflow-SEI, 48 h episodes (cfg3)"),
+    "cfg4": dict(use_case="ut", evs=50, envs=65536, episode_hours=48, minutes=60,
+                 over=dict(include_building=False, include_pv=False),
+                 label="utility fleet, 50 EVs, V2G, spot price + feed-in tariff, 1-hour resolution, price-only observer (cfg4)"),
+    "cfg4full": dict(use_case="ut", evs=50, envs=65536, episode_hours=48, minutes=60, over={},
+                     label="utility fleet, 50 EVs, V2G, 1-hour resolution, full observer (cfg4 variant)"),
+    "cfg5": dict(use_case="lmd", evs=50, total_envs=1048576, episode_hours=24, minutes=15, over={},
+                 label="LMD fleet, 50 EVs, 1,048,576 envs sharded over the GPUs (cfg5 env step; the PPO-style rollout "
+                       "through FleetVecEnv is scripts/rollout_cfg5.py)"),
+}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
-    ap.add_argument("--evs", type=int, default=50)
-    ap.add_argument("--use-case", default="lmd")
-    ap.add_argument("--episode-hours", type=int, default=24)
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS),
+                    help="BASELINE.json workload (cfg2 = configs[1], the one the metric is quoted on)")
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the config's)")
+    ap.add_argument("--evs", type=int, default=None)
+    ap.add_argument("--use-case", default=None)
+    ap.add_argument("--episode-hours", type=int, default=None)
     ap.add_argument("--carry", type=int, default=1, help="carry_degradation_state (1 = reference object semantics)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-envs", type=int, default=2048)
-    return ap.parse_args()
+    args = ap.parse_args()
+    cf = CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.envs is None:
+        args.envs = cf["total_envs"] // world if "total_envs" in cf else cf["envs"]
+    for k in ("evs", "use_case", "episode_hours"):
+        if getattr(args, k) is None:
+            setattr(args, k, cf[k])
+    args.scaling = "strong" if "total_envs" in cf else "weak"
+    args.cfg = cf
+    return args
 
 
 def build_workload(args):
@@ -60,7 +89,10 @@ def build_workload(args):
 
     sched = generate_schedule(args.use_case, args.evs, seed=42)
     price, tariff, load, pv = synthetic_series(seed=7)
-    cfg = default_config(args.use_case, episode_length=args.episode_hours, seed=0)
+    over = dict(args.cfg["over"])
+    if args.cfg["minutes"] == 60:
+        over.update(freq="1h", minutes=60, time_steps_per_hour=1)
+    cfg = default_config(args.use_case, episode_length=args.episode_hours, seed=0, **over)
     built = build_fleet(cfg, FleetInputs(sched, price, tariff, load, pv), auto_reset=True,
                         carry_degradation_state=bool(args.carry), seed=0, time_picker="random")
     return built
@@ -197,8 +229,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "EV-steps/sec", "value": value, "unit": "EV-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, built, D),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args, built, D), envs_per_step_timed=E,
+                       sample=f"bounded sample: {E} of the {args.envs} envs per step (the per-env work is identical)"),
         "cpu_baseline": {"value": value, "unit": "EV-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "EV-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference FleetEnv is pure Python/pandas (≈35-85 EV-steps/s/core measured in the build container, "
@@ -208,11 +241,12 @@ def run_reference(args):
 
 
 def workload_config(args, built, D):
-    return {"workload": f"{args.use_case} fleet {args.evs} EVs x {args.envs} envs/GPU, rainflow-SEI degradation, "
-                        f"15-min steps, {args.episode_hours} h episodes, full observer (cfg2)",
+    return {"workload": f"{args.cfg['label']}; {args.envs} envs/GPU", "name": args.config,
             "envs_per_gpu": args.envs, "evs": args.evs, "obs_dim": D, "table_len": int(built.consts.table_len),
             "episode_steps": int(built.consts.episode_steps), "auto_reset": True,
             "carry_degradation_state": bool(args.carry),
+            "episode_phase": "de-phased: env e is (e mod episode_steps) steps into its episode when timing starts, so "
+                             "every step sees ~E/episode_steps auto-resets and ~E/96 daily evaluations (SB3 steady state)",
             "l2_policy": "per-step working set (actions+state+obs ≈ 0.27 GB at cfg2) exceeds the 126 MB L2; "
                          "action tensors rotate through a ring"}
 
@@ -262,8 +296,15 @@ def main():
     # alone (tens of ms) would be shorter than nvidia-smi's sampling period
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # run one simulated day first so that the timed region sees the steady state (auto-resets, daily evaluations)
-    for s in range(W + built.consts.episode_steps):
+    # De-phase the envs, then warm up: a synchronous reset would leave all envs at the same episode step (no resets for
+    # L-1 steps, then all at once).  Env e is re-reset after step (e mod L) of the first L steps, so that when timing
+    # starts the episode ages are uniform over 0..L-1 — what a long SB3 rollout converges to.
+    L = int(built.consts.episode_steps)
+    phase = torch.arange(E, device=dev, dtype=torch.int64) % L
+    for s in range(L):
+        h.step_unchecked(ptrs[s % 8], o_p, r_p, d_p, t_p, sp)
+        h.reset(mask=(phase == s).to(torch.uint8), obs=obs)
+    for s in range(W):
         h.step_unchecked(ptrs[s % 8], o_p, r_p, d_p, t_p, sp)
     torch.cuda.synchronize(dev)
     h.reset_stats()
@@ -317,7 +358,7 @@ def main():
                 "algorithmic_bytes_per_ev_step": b_alg(N, D), "kernel": h.step_kernel_name,
                 "kernel_ms": step_kernel_ms, "post_kernel_ms": post_kernel_ms, "timed_launches": nt,
                 "whole_step": {"achieved": whole, "frac": whole / peak, "ms": ms_per_step,
-                               "note": "step kernel + post kernel (daily degradation, auto-reset) + launch gaps"}}
+                               "note": "step kernel + post kernel (rainflow consumption, daily degradation, auto-reset) + launch gaps"}}
 
     # end to end through the host-buffer C-ABI call
     e2e = None
@@ -352,7 +393,7 @@ def main():
                        "n_viol", "degradation"], stats.cpu().tolist()))
         line = {
             "metric": "EV-steps/sec", "value": value, "unit": "EV-steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, built, D),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "device_bytes": h.device_bytes, "device_error_flags": err,

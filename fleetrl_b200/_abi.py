@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FLEET_DEG_SEI = 0
 FLEET_DEG_EMPIRICAL = 1
@@ -20,7 +20,8 @@ class FleetConsts(C.Structure):
         ("bl_pv_lookahead", C.c_int32), ("include_price", C.c_int32), ("include_building", C.c_int32),
         ("include_pv", C.c_int32), ("aux", C.c_int32), ("normalize", C.c_int32), ("is_caretaker", C.c_int32),
         ("calc_degradation", C.c_int32), ("deg_mode", C.c_int32), ("carry_degradation_state", C.c_int32),
-        ("auto_reset", C.c_int32), ("start_lo", C.c_int32), ("start_hi", C.c_int32), ("reserved0", C.c_int32),
+        ("auto_reset", C.c_int32), ("start_lo", C.c_int32), ("start_hi", C.c_int32),
+        ("rf_ring_rows", C.c_int32), ("rf_stack_depth", C.c_int32), ("reserved0", C.c_int32),
         ("seed", C.c_uint64),
         ("dt", C.c_double),
         ("init_battery_cap", C.c_double), ("obc_max_power", C.c_double), ("charging_eff", C.c_double),
@@ -39,7 +40,7 @@ class FleetConsts(C.Structure):
 
     INT_FIELDS = ("num_evs table_len steps_per_hour episode_steps price_lookahead bl_pv_lookahead include_price "
                   "include_building include_pv aux normalize is_caretaker calc_degradation deg_mode "
-                  "carry_degradation_state auto_reset start_lo start_hi seed").split()
+                  "carry_degradation_state auto_reset start_lo start_hi rf_ring_rows rf_stack_depth seed").split()
 
     def to_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -78,23 +78,16 @@ struct __align__(16) StepRow {
 };
 static_assert(sizeof(StepRow) == 64, "StepRow must be 64 bytes");
 
-struct TmaLayout {
-    int act, soc, hl, soh, hist, rec, hdr, row, in_bytes;      // one input stage
-    int o_soc, o_hl, o_hist, o_obs, out_bytes;                 // one output buffer
-    int in0, out0, contrib, contrib_bytes, sums, bars, total;  // per CTA
-};
-
 struct StepParams {
     // sizes
-    int E, N, T, R, L, D, Ha, Hb, hdr_stride, B;
+    int E, N, T, R, Rm, L, D, Ha, Hb, hdr_stride, B;   // R: rows of the soc_deg history ring (power of two), Rm = R - 1
     unsigned long long RN;    // R * N
     unsigned int n_magic;     // ceil(2^32 / N): j / N == __umulhi(j, n_magic) for j < 2^16
     unsigned int h_magic;     // same for the header length Ha+Hb
     int off_contrib, off_obs; // byte offsets of the contribution arrays / obs tile in dynamic shared memory
     // flags
     int is_ct, calc_deg, deg_mode, carry, auto_reset, bulk_ok;
-    int Bt;                   // envs per tile of the TMA kernel (0 = TMA path not applicable)
-    TmaLayout tl;             // shared-memory layout of the TMA kernel
+    int rf_on;                // incremental rainflow state is maintained (calc_deg && deg_mode == FLEET_DEG_SEI)
     int start_lo, start_hi;
     unsigned long long seed;
     long long env_id_offset;
@@ -108,39 +101,39 @@ struct StepParams {
     const StepRow* step_row;  // [T]
     const float* hdr;         // [T][hdr_stride]
     // state
-    int4* env4;               // [E] {t, t_start, ep_count, unused}
+    int4* env4;               // [E] {t, t_start, ep_count, k_done}: k_done = newest history sample the rainflow state has consumed
     double* soc;              // [E][N]
     float* hl;                // [E][N]
     double* soh;              // [E][N]
-    double* hist;             // [E][R][N] soc_deg history (row k = soc_deg after k steps of the episode)
+    double* hist;             // [E][R][N] ring of soc_deg samples: sample k of the episode lives in row k & Rm
     uint8_t* tflip;           // [E][N] target_soc raised to 0.9 (fleet_environment.py:613-614)
     int* n_flips;             // [1] number of set tflip bytes (0 => the array is never read)
     double* env_f64;          // [6][E] ep_return, last_ep_return, reward64, cashflow, overload, soc_viol
-    int* rf_len;              // [E][N]
+    int* rf_len;              // [E][N] RainflowSeiDegradation.rainflow_length
     double* fd_cyc;           // [E][N]
     double* life;             // [E][N]
     int* n_cycles;            // [E][N]
     double* last_deg;         // [E][N]
+    // incremental rainflow: the three-point stack of rainflow.extract_cycles persists per vehicle
+    int rf_S, rf_X, rf_P;     // inline stack entries per vehicle, entries per extension slot, number of extension slots
+    double* rf_stack;         // [E][S][N] committed reversal points still on the stack (entry 0 = bottom)
+    unsigned int* rf_dc;      // [E][N] stack depth | committed cycles of the episode << 16
+    double2* rf_acc;          // [E][N] {sum of the means of the committed cycles, stress sum of those at list positions >= rainflow_length-1}
+    int* rf_ext;              // [E][N] extension slot holding stack entries >= S, or -1
+    int* ext_owner;           // [P] vehicle index owning the slot, or -1
+    double* ext_val;          // [P][X]
     double* charge_log;       // [E][N] or nullptr: energy into (+) / out of (-) each battery in the last step
     double* stats;            // [kStatStripes][FLEET_S__COUNT]
     unsigned int* err_flags;  // [1]
     const int* next_start;    // [E] or nullptr
-    int2* wl;                 // [E] work list of the post kernel, degradation entries: {env, WL_* flags}
-    int* wlr;                 // [E] work list of the post kernel, reset-only entries: env
-    int* wl_count;            // [4] {degradation entries, reset-only entries, next degradation entry, next reset entry}
+    int2* wl;                 // [E] work list of the post kernel: {env, WL_* flags}
+    int* wl_count;            // [4] {entries, next entry to fetch, -, -}
     unsigned int* wl_done;    // [1]
     // persistent step kernel geometry (host-computed so that the kernel reads it from the constant bank, not registers)
     int pf_B, pf_bulk, pf_ntiles, pf_cslots, pf_cper, pf_pair;      // pf_B: envs per tile = kPfCompute / N
     unsigned int pf_tile_hist;                                // B * RN: history elements per tile (< 2^32, checked at create)
     int pf_envs_b, pf_contrib_b, pf_obs_b;                    // bytes of one env-scratch / contribution / obs buffer
     int pf_off_contrib, pf_off_sums, pf_off_obs, pf_off_stage;   // shared-memory offsets
-    int po_nch;               // chunks (work items) per degradation entry: vehicles [k*po_nc, (k+1)*po_nc)
-    int* wl_chunk_cnt;        // [E] finished chunks per entry (only for entries that also reset)
-    int po_nc, po_lp, po_g;   // cooperative post kernel: vehicles per chunk, column pitch (odd), threads per vehicle in pass 2
-    int po_stk, po_recs, po_misc;   // its shared-memory offsets (bytes)
-    double* post_scratch_v;   // [grid_post][scratch_cap][64] fallback rainflow value ring
-    uint16_t* post_scratch_i; // [grid_post][scratch_cap][64]
-    int scratch_cap;          // power of two >= L+2
     // I/O
     const float* actions;
     float* obs;
@@ -158,6 +151,7 @@ struct EnvS {  // per-env scratch of a tile, shared memory
     int t, t_start, ep_count, flags;
     double S, F_cr, F_dr, Rfac, pv_share, gml, pvv;
     float* obs_dst;
+    int k_done;
 };
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
@@ -300,7 +294,16 @@ __device__ __forceinline__ void reset_slot(const StepParams& p, int e, int n, in
     p.soc[i] = soc;
     p.hl[i] = hl;
     p.soh[i] = soh;
-    p.hist[((size_t)e * p.R + 0) * p.N + n] = sdeg;
+    p.hist[((size_t)e * p.R + 0) * p.N + n] = sdeg;                 // LogDataDeg.soc_log restarts with this sample
+    if (p.rf_on) {
+        // rainflow state of the new episode: the first sample is the first point on the stack, no cycles yet
+        // (the rainflow_length / fd_cyc / l members above survive unless reinit_deg)
+        const int slot = p.rf_ext[i];
+        if (slot >= 0) { atomicExch(&p.ext_owner[slot], -1); p.rf_ext[i] = -1; }
+        p.rf_stack[((size_t)e * p.rf_S + 0) * p.N + n] = sdeg;
+        p.rf_dc[i] = 1u;
+        p.rf_acc[i] = make_double2(0.0, 0.0);
+    }
     if (obs_row) {
         write_ev_obs<kNorm, kAux>(p, obs_row, n, soc, hl, rec, flip);
         copy_hdr<kAux>(p, obs_row, n, t0);
@@ -308,198 +311,185 @@ __device__ __forceinline__ void reset_slot(const StepParams& p, int e, int n, in
 }
 
 // ------------------------------------------------------------------------------------------------ degradation
-// rainflow 3.2.0 extract_cycles (ASTM E1049-85 three-point method) over one vehicle's SOC history, feeding
-// RainflowSeiDegradation.calculate_degradation (rainflow_sei_degradation.py:128-206).
+// rainflow 3.2.0 extract_cycles (ASTM E1049-85 three-point method) feeding RainflowSeiDegradation.calculate_degradation
+// (rainflow_sei_degradation.py:128-206), INCREMENTALLY.
 //
-// Pass 1 (divergent by nature, kept lean): the reversal scan and the three-point stack.  The stack holds
-//   (sample index, value) pairs in a small shared-memory ring, the top three entries are mirrored in registers;
-//   every emitted cycle is recorded as one 32-bit word (i_a | i_b << 15 | full << 30) in shared memory and its
-//   mean is accumulated (the reference averages the means of ALL cycles, :140).
-// Pass 2 (convergent): the reference takes the POSITIONAL slice [rainflow_length-1 : len-1] of the full cycle list
-//   (:146); the recorded cycles a <= j < m-1 are replayed in list order and the SEI stress terms (pow/exp) are
-//   evaluated with all lanes of the warp active.
-// max(End) of the list is always len-1 (the provisional last reversal closes the last half cycle), :138.
-#ifdef POST_TIMING
-__device__ unsigned long long g_post_clk[16];
-#define PT_MARK(k) do { if ((threadIdx.x & 31) == 0) { const long long _c = clock64(); atomicAdd(&g_post_clk[k], (unsigned long long)(_c - _pt)); _pt = _c; } } while (0)
-#define PT_START() long long _pt = clock64()
-#else
-#define PT_MARK(k) do {} while (0)
-#define PT_START() do {} while (0)
-#endif
-constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one work-list env per CTA)
-constexpr int kStackS = 16;   // shared-memory ring depth; deeper stacks fall back to a global-memory scratch ring
+// The reference re-runs extract_cycles over the whole soc_log of the episode at every daily evaluation.  Both halves of
+// that algorithm are streaming: reversals() is causal except for the provisional last sample, and the three-point stack
+// only ever looks at its top three points.  So per vehicle the committed state is kept in HBM between evaluations:
+//   * the stack of reversal points that have not been paired off yet (values only; entry 0 = bottom),
+//   * c = number of cycles emitted so far (they form a stable prefix of the list the reference would build),
+//   * the running sum of their means (the reference averages the means of ALL cycles, :140),
+//   * the stress sum of those committed cycles whose list position is >= rainflow_length-1, i.e. the part of the
+//     positional slice [rainflow_length-1 : len-1] (:146) that is already final.
+// The step kernel only appends soc_deg samples to a small per-env ring (hist).  The post kernel consumes the ring
+// (at the daily trigger, or earlier when the ring is about to wrap): reversal detection continues from the last
+// consumed sample (the direction of the last non-zero difference is the sign of x_cur - top of stack, because the top
+// of the stack is always the most recently yielded reversal), reversals are pushed, closed cycles are committed.
+// An evaluation then pushes the provisional end point onto a READ-ONLY view of the stack and counts the residue.
+constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one work-list env per CTA, one vehicle per thread)
+constexpr int kRfBatch = 8;        // history rows fetched per batch (independent loads in flight)
 
-struct RfRing {               // stack storage: entry k lives at [(k & mask) * stride]
-    double* v;
-    uint16_t* i;
-    int mask, stride;
-};
-
-struct RfOut { int m; double mean_sum; bool overflow; };
-
-constexpr int kRfBatch = 16;  // history samples / reversal values prefetched per batch (independent loads in flight)
-
-// Two phases, both streaming the history with batched prefetch:
-//  A. reversal detection (rainflow.reversals): branch-free per sample; the sample indices of the reversal points are
-//     compacted into `ridx` (shared memory, one 16-bit entry per point).  First and last samples are reversals;
-//     plateaus are skipped with an exact ==; the index reported for a plateau is its last sample.
-//  B. the three-point stack (rainflow.extract_cycles) over the compacted reversal list only, values fetched by
-//     index in batches.
-// kShared: ring in shared memory with compile-time geometry (mask kStackS-1, stride kPostThreads).
-template <bool kShared>
-__device__ __forceinline__ RfOut rainflow_pass1(const double* __restrict__ x, int xstride, int len, RfRing rg,
-                                                uint32_t* __restrict__ recs, uint16_t* __restrict__ ridx) {
-    RfOut out; out.m = 0; out.mean_sum = 0; out.overflow = false;
-    if (len < 2) return out;
-    const int mask = kShared ? (kStackS - 1) : rg.mask;
-    const int stride = kShared ? kPostThreads : rg.stride;
-    const int cap_ring = mask + 1;
-    PT_START();
-
-    // ---- phase A
-    int nr = 0;                                   // reversal points found so far
-    ridx[0] = 0; nr = 1;                          // yield (0, x0)
-    {
-        const double x0 = __ldcs(x), x1 = __ldcs(x + xstride);
-        double xc = x1, d_last = x1 - x0;
-        for (int pos0 = 2; pos0 < len; pos0 += kRfBatch) {
-            double xb[kRfBatch];
-#pragma unroll
-            for (int u = 0; u < kRfBatch; u++)   // clamped index, no select: all loads of the batch issue back to back
-                xb[u] = __ldcs(x + (size_t)min(pos0 + u, len - 1) * xstride);
-#pragma unroll
-            for (int u = 0; u < kRfBatch; u++) {
-                const int pos = pos0 + u;
-                const double x_next = xb[u];
-                const bool ne = (pos < len) && (x_next != xc);
-                const double d_next = x_next - xc;
-                const bool rev = ne && (d_last * d_next < 0);
-                if (rev) { ridx[nr * kPostThreads] = (uint16_t)(pos - 1); nr++; }
-                if (ne) { xc = x_next; d_last = d_next; }
-            }
-        }
-        if (len >= 3) { ridx[nr * kPostThreads] = (uint16_t)(len - 1); nr++; }   // the last sample closes the series
-    }
-
-    PT_MARK(0);
-    // ---- phase B
-    int lo = 0, hi = 0, m = 0;
-    double mean_sum = 0;
-    double v1 = 0, v2 = 0, v3 = 0;     // values of the top three stack entries (v3 = top)
-    int i1 = 0, i2 = 0, i3 = 0;        // their sample indices
-    bool overflow = false;
-#define RF_SLOT(k) (((k) & mask) * stride)
-#define RF_EMIT(ia, xa, ib, xb_, full)                                                           \
-    do {                                                                                         \
-        mean_sum += 0.5 * ((xa) + (xb_));                                                        \
-        recs[m * kPostThreads] = (uint32_t)(ia) | ((uint32_t)(ib) << 15) | ((uint32_t)(full) << 30);  \
-        m++;                                                                                     \
-    } while (0)
-    for (int r0 = 0; r0 < nr && !overflow; r0 += kRfBatch) {
-        double vb[kRfBatch];
-        int ib_[kRfBatch];
-#pragma unroll
-        for (int u = 0; u < kRfBatch; u++) ib_[u] = (int)ridx[min(r0 + u, nr - 1) * kPostThreads];
-#pragma unroll
-        for (int u = 0; u < kRfBatch; u++) vb[u] = x[(size_t)ib_[u] * xstride];
-#pragma unroll
-        for (int u = 0; u < kRfBatch; u++) {
-            if (r0 + u < nr && !overflow) {
-                const double val = vb[u];
-                const int idx = ib_[u];
-                if (hi - lo >= cap_ring) { overflow = true; }
-                else {
-                    rg.v[RF_SLOT(hi)] = val; rg.i[RF_SLOT(hi)] = (uint16_t)idx; hi++;
-                    v1 = v2; i1 = i2; v2 = v3; i2 = i3; v3 = val; i3 = idx;
-                    while (hi - lo >= 3) {
-                        const double X = fabs(v3 - v2), Y = fabs(v2 - v1);
-                        if (X < Y) break;
-                        if (hi - lo == 3) { RF_EMIT(i1, v1, i2, v2, 0); lo++; }
-                        else {
-                            RF_EMIT(i1, v1, i2, v2, 1);
-                            hi -= 2;
-                            rg.v[RF_SLOT(hi - 1)] = v3; rg.i[RF_SLOT(hi - 1)] = (uint16_t)i3;
-                            v2 = rg.v[RF_SLOT(hi - 2)]; i2 = rg.i[RF_SLOT(hi - 2)];
-                            if (hi - lo >= 3) { v1 = rg.v[RF_SLOT(hi - 3)]; i1 = rg.i[RF_SLOT(hi - 3)]; }
-                        }
-                    }
-                }
-            }
-        }
-    }
-    PT_MARK(1);
-    while (hi - lo > 1 && !overflow) {
-        const double xa = rg.v[RF_SLOT(lo)], xb2 = rg.v[RF_SLOT(lo + 1)];
-        const int ia = rg.i[RF_SLOT(lo)], ib2 = rg.i[RF_SLOT(lo + 1)];
-        RF_EMIT(ia, xa, ib2, xb2, 0);
-        lo++;
-    }
-#undef RF_EMIT
-#undef RF_SLOT
-    PT_MARK(2);
-#ifdef POST_TIMING
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&g_post_clk[8], (unsigned long long)nr); atomicAdd(&g_post_clk[9], (unsigned long long)m); atomicAdd(&g_post_clk[10], 1ull); }
-#endif
-    out.m = m; out.mean_sum = mean_sum; out.overflow = overflow;
-    return out;
+// SEI stress of one cycle: rainflow_sei_degradation.py:68-79 with effective DoD = clip(range*count, 0, 1) (:170)
+__device__ __forceinline__ double sei_cycle_stress(double range, double count, double mean, double s_temp) {
+    const double k_sigma = 1.04, sigma_ref = 0.5, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
+    double eff = range * count;
+    eff = eff < 0 ? 0 : (eff > 1 ? 1 : eff);
+    const double s_dod = 1.0 / (kd1 * pow(eff, kd2) + kd3);                    // :68  (dod == 0 -> inf -> 0)
+    const double s_soc = exp(k_sigma * (mean - sigma_ref));                    // :70
+    return s_dod * s_soc * s_temp;                                             // :77-79
 }
 
-// RainflowSeiDegradation.calculate_degradation for one vehicle, given pass 1's result.  Returns the SOH loss.
-__device__ __forceinline__ double sei_finish(const StepParams& p, size_t i, const double* __restrict__ x, int xstride,
-                                             int len, const RfOut r, const uint32_t* __restrict__ recs) {
-    const double alpha_sei = 5.75E-2, beta_sei = 121, k_sigma = 1.04, sigma_ref = 0.5, k_temp = 6.93E-2,
-                 temp_ref = 25, k_dt = 4.14E-10, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
-    PT_START();
-    const int rf_len = p.rf_len[i];
-    const int m = r.m;
-    p.n_cycles[i] = m;
-    double deg = 0;
-#ifdef POST_TIMING
-    if ((threadIdx.x & 31) == 0 && m > rf_len) atomicAdd(&g_post_clk[11], (unsigned long long)(m - rf_len));
-#endif
-    if (m > rf_len) {                                                                  // :143
-        const double s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
-        double fsum = 0, max_dod = 0;
-        for (int j = rf_len - 1; j < m - 1; j++) {                                     // iloc[rf_len-1 : len-1], :146
-            const uint32_t rec = recs[j * kPostThreads];
-            const double xa = x[(size_t)(rec & 0x7fffu) * xstride], xb = x[(size_t)((rec >> 15) & 0x7fffu) * xstride];
-            const double range = fabs(xa - xb), mean = 0.5 * (xa + xb);
-            double eff = range * ((rec >> 30) ? 1.0 : 0.5);                            // :170
-            eff = eff < 0 ? 0 : (eff > 1 ? 1 : eff);
-            const double s_dod = 1.0 / (kd1 * pow(eff, kd2) + kd3);                    // :68  (dod == 0 -> inf -> 0)
-            const double s_soc = exp(k_sigma * (mean - sigma_ref));                    // :70
-            fsum += s_dod * s_soc * s_temp;                                            // :77-79, np.sum :174
-            if (range > max_dod) max_dod = range;
-        }
-        PT_MARK(3);
-        const double battery_age = (double)(len - 1) * p.dt * 3600;                    // :138  max(End) == len-1
-        const double mean_soc_cal = r.mean_sum / (double)m;                            // :140
-        if (max_dod > 5) atomicOr(p.err_flags, 4u);                                    // :164-167
-        const double fd_cal = (k_dt * battery_age) * exp(k_sigma * (mean_soc_cal - sigma_ref)) * s_temp;  // :81-83
-        const double fd_cyc = p.fd_cyc[i] + fsum;                                      // :174
-        p.fd_cyc[i] = fd_cyc;
-        const double fd = fd_cyc + fd_cal;
-        const double l_old = p.life[i];
-        double new_l;
-        if (p.init_soh == 1.0) {
-            new_l = 1 - alpha_sei * exp(-beta_sei * fd) - (1 - alpha_sei) * exp(-fd);  // :85-86
-            if (new_l < 0) atomicOr(p.err_flags, 2u);                                  // :179-180
-        } else {
-            new_l = 1 - (1 - l_old) * exp(-fd);                                        // :89,186
-        }
-        deg = new_l - l_old;                                                           // :189
-        p.life[i] = new_l;                                                             // :192
-        p.rf_len[i] = m;                                                               // :195
+// Claim a stack extension slot for vehicle `vid` (open addressing over the owner table; rare path).
+__device__ __noinline__ int rf_ext_alloc(const StepParams& p, size_t vid) {
+    const unsigned P = (unsigned)p.rf_P;
+    if (P == 0) return -1;
+    unsigned q = (unsigned)(mix64((unsigned long long)vid) % P);
+    for (unsigned k = 0; k < P; k++) {
+        if (atomicCAS(&p.ext_owner[q], -1, (int)vid) == -1) return (int)q;
+        if (++q == P) q = 0;
     }
-    PT_MARK(4);
+    return -1;
+}
+
+// One vehicle of a post-kernel entry: consume history samples k_done+1 .. k_now, then (evaluate) run
+// RainflowSeiDegradation.calculate_degradation.  smcol: this thread's column of the shared-memory stack copy
+// (entry s at smcol[s * kPostThreads]), revcol: its column of the per-batch reversal list.  Returns the SOH loss.
+__device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, int k_done, int k_now, bool evaluate,
+                                             double s_temp, double* __restrict__ smcol, double* __restrict__ revcol) {
+    const int N = p.N, S = p.rf_S, X = p.rf_X, Rm = p.Rm;
+    const size_t i = (size_t)e * N + n;
+    const unsigned int dc = p.rf_dc[i];
+    int depth = (int)(dc & 0xffffu), c = (int)(dc >> 16);
+    double2 acc = p.rf_acc[i];                               // x: sum of committed means, y: pending stress sum
+    int slot = p.rf_ext[i];
+    const int rfl = p.rf_len[i];
+    const double* __restrict__ hcol = p.hist + (size_t)e * p.RN + n;          // sample k at hcol[(k & Rm) * N]
+    double* __restrict__ stk = p.rf_stack + (size_t)e * S * N + n;            // entry s at stk[s * N]
+    double* ext = slot >= 0 ? p.ext_val + (size_t)slot * X : nullptr;
+    double x_cur = __ldcs(hcol + (size_t)(k_done & Rm) * N);
+    {
+        const int ds = depth < S ? depth : S;
+        for (int s = 0; s < ds; s++) smcol[s * kPostThreads] = stk[(size_t)s * N];
+    }
+    bool bad = false;
+#define RF_GET(s_) ((s_) < S ? smcol[(s_) * kPostThreads] : ext[(s_) - S])
+#define RF_SET(s_, v_) do { if ((s_) < S) smcol[(s_) * kPostThreads] = (v_); else ext[(s_) - S] = (v_); } while (0)
+    double max_dod = 0;
+    // cycle (xa, xb) with count `cnt` leaves the stack for good: list position c
+#define RF_COMMIT(xa, xb, cnt)                                                                 \
+    do {                                                                                       \
+        const double range_ = fabs((xa) - (xb)), mean_ = 0.5 * ((xa) + (xb));                  \
+        acc.x += mean_;                                                                        \
+        if (c >= rfl - 1) { acc.y += sei_cycle_stress(range_, (cnt), mean_, s_temp); max_dod = fmax(max_dod, range_); } \
+        c++;                                                                                   \
+    } while (0)
+    double dsg = x_cur - RF_GET(depth - 1);                  // sign of the last non-zero difference (0: none yet)
+    for (int r0 = k_done + 1; r0 <= k_now; r0 += kRfBatch) {
+        // rainflow.reversals over this batch of samples: values of the reversal points -> revcol
+        double xb[kRfBatch];
+#pragma unroll
+        for (int u = 0; u < kRfBatch; u++) xb[u] = __ldcs(hcol + (size_t)(min(r0 + u, k_now) & Rm) * N);
+        int nrev = 0;
+#pragma unroll
+        for (int u = 0; u < kRfBatch; u++) {
+            const double x_next = xb[u];
+            if (r0 + u <= k_now && x_next != x_cur) {
+                const double d = x_next - x_cur;
+                if ((dsg < 0 && d > 0) || (dsg > 0 && d < 0)) { revcol[nrev * kPostThreads] = x_cur; nrev++; }
+                dsg = d; x_cur = x_next;
+            }
+        }
+        // rainflow.extract_cycles: push each reversal, close cycles while the newest range is not smaller
+        for (int q = 0; q < nrev; q++) {
+            const double v = revcol[q * kPostThreads];
+            if (depth >= S && !ext) {
+                slot = (depth < S + X) ? rf_ext_alloc(p, i) : -1;
+                if (slot >= 0) ext = p.ext_val + (size_t)slot * X;
+            }
+            if (depth >= S + X || (depth >= S && !ext)) { bad = true; continue; }   // capacity exceeded: flagged below
+            RF_SET(depth, v); depth++;
+            while (depth >= 3) {
+                const double x3 = RF_GET(depth - 1), x2 = RF_GET(depth - 2), x1 = RF_GET(depth - 3);
+                if (fabs(x3 - x2) < fabs(x2 - x1)) break;
+                if (depth == 3) { RF_COMMIT(x1, x2, 0.5); RF_SET(0, x2); RF_SET(1, x3); depth = 2; }   // popleft
+                else { RF_COMMIT(x1, x2, 1.0); RF_SET(depth - 3, x3); depth -= 2; }
+            }
+        }
+    }
+    if (bad) atomicOr(p.err_flags, 8u);
+
+    double deg = 0;
+    if (evaluate) {
+        const double alpha_sei = 5.75E-2, beta_sei = 121, k_sigma = 1.04, sigma_ref = 0.5, k_dt = 4.14E-10;
+        const int len = k_now + 1;                           // samples in the reference's soc_log
+        int m = c;
+        double msum = acc.x, fs = 0;
+        if (len >= 3) {
+            // the last sample is always yielded as a (provisional) reversal: x_cur on top of a read-only view
+            // stack[lo .. h) of the committed points
+            int h = depth, lo = 0;
+#define RF_PROV(xa, xb, cnt, last_)                                                            \
+    do {                                                                                       \
+        const double range_ = fabs((xa) - (xb)), mean_ = 0.5 * ((xa) + (xb));                  \
+        msum += mean_;                                                                         \
+        if (!(last_) && m >= rfl - 1) { fs += sei_cycle_stress(range_, (cnt), mean_, s_temp); max_dod = fmax(max_dod, range_); } \
+        m++;                                                                                   \
+    } while (0)
+            while (h - lo >= 2) {
+                const double x2 = RF_GET(h - 1), x1 = RF_GET(h - 2);
+                if (fabs(x_cur - x2) < fabs(x2 - x1)) break;
+                if (h - lo == 2) { RF_PROV(x1, x2, 0.5, false); lo++; }
+                else { RF_PROV(x1, x2, 1.0, false); h -= 2; }
+            }
+            // "count the remaining ranges as one-half cycles", bottom first; the last of them is position m-1 of the
+            // list, which the slice [rainflow_length-1 : len-1] never includes
+            for (int k = lo; k + 1 < h; k++) RF_PROV(RF_GET(k), RF_GET(k + 1), 0.5, false);
+            RF_PROV(RF_GET(h - 1), x_cur, 0.5, true);
+#undef RF_PROV
+        }
+        p.n_cycles[i] = m;
+        if (m > rfl) {                                                                     // :143
+            const double fsum = acc.y + fs;                                                // np.sum over the slice, :174
+            const double battery_age = (double)(len - 1) * p.dt * 3600;                    // :138  max(End) == len-1
+            const double mean_soc_cal = msum / (double)m;                                  // :140
+            if (max_dod > 5) atomicOr(p.err_flags, 4u);                                    // :164-167
+            const double fd_cal = (k_dt * battery_age) * exp(k_sigma * (mean_soc_cal - sigma_ref)) * s_temp;  // :81-83
+            const double fd_cyc = p.fd_cyc[i] + fsum;                                      // :174
+            p.fd_cyc[i] = fd_cyc;
+            const double fd = fd_cyc + fd_cal;
+            const double l_old = p.life[i];
+            double new_l;
+            if (p.init_soh == 1.0) {
+                new_l = 1 - alpha_sei * exp(-beta_sei * fd) - (1 - alpha_sei) * exp(-fd);  // :85-86
+                if (new_l < 0) atomicOr(p.err_flags, 2u);                                  // :179-180
+            } else {
+                new_l = 1 - (1 - l_old) * exp(-fd);                                        // :89,186
+            }
+            deg = new_l - l_old;                                                           // :189
+            p.life[i] = new_l;                                                             // :192
+            p.rf_len[i] = m;                                                               // :195
+            acc.y = 0;                       // committed cycles below position m-1 can never be in a later slice
+        }
+        p.last_deg[i] = deg;
+        p.soh[i] = p.soh[i] - deg;                                                         // :671 (battery_cap is derived, :673)
+    }
+#undef RF_COMMIT
+    {
+        const int ds = depth < S ? depth : S;
+        for (int s = 0; s < ds; s++) stk[(size_t)s * N] = smcol[s * kPostThreads];
+    }
+#undef RF_GET
+#undef RF_SET
+    if (slot >= 0 && depth <= S) { atomicExch(&p.ext_owner[slot], -1); slot = -1; }
+    p.rf_dc[i] = (unsigned int)depth | ((unsigned int)c << 16);
+    p.rf_acc[i] = acc;
+    p.rf_ext[i] = slot;
     return deg;
 }
 
 // EmpiricalDegradation.calculate_degradation for one vehicle (empirical_degradation.py:60-94).
-__device__ __forceinline__ double empirical_eval(double dt, double evse, int N, const double* __restrict__ hcol, int len) {
-    const double old_soc = hcol[(size_t)(len - 2) * N];
-    const double new_soc = hcol[(size_t)(len - 1) * N];
+__device__ __forceinline__ double empirical_eval(double dt, double evse, double old_soc, double new_soc) {
     const double avg_soc = (old_soc + new_soc) / 2;
     const double cs[3] = {0, 40, 90};
     const double ca[3] = {0.0065, 0.0293, 0.065};
@@ -647,12 +637,16 @@ __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es
 
 // ------------------------------------------------------------------------------------------------ step kernel
 // Work-list entry pushed by the step kernel for envs that need the post kernel (daily degradation and/or reset).
-constexpr int WL_TRIGGER = 1, WL_RESET = 2;
-// Envs with a degradation evaluation (possibly followed by a reset) and envs that only reset go to separate lists:
-// the first kind is one CTA's worth of cooperative work each, the second a quarter CTA's.
+constexpr int WL_TRIGGER = 1, WL_RESET = 2, WL_FLUSH = 4;
 __device__ __forceinline__ void wl_push(const StepParams& p, int e, int wf) {
-    if (wf & WL_TRIGGER) p.wl[atomicAdd(p.wl_count, 1)] = make_int2(e, wf);
-    else p.wlr[atomicAdd(p.wl_count + 1, 1)] = e;
+    p.wl[atomicAdd(p.wl_count, 1)] = make_int2(e, wf);
+}
+// Work-list flags of an env whose step k (history sample k+1) has just been taken.  WL_FLUSH: with the next sample the
+// ring would hold more than R rows (samples k_done .. k+2), so the pending ones are consumed now.
+__device__ __forceinline__ int wl_flags(const StepParams& p, int env_flags, int k, int k_done) {
+    int wf = ((env_flags & EF_TRIGGER) ? WL_TRIGGER : 0) | ((env_flags & EF_RESET) ? WL_RESET : 0);
+    if (p.rf_on && k + 1 - k_done >= p.R - 1) wf |= WL_FLUSH;
+    return wf;
 }
 
 // Shared-memory layout (dynamic): EnvS envs[B] | double contrib[kNQ][slots] | double sums[kNQ][B] |
@@ -691,7 +685,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
         const int e = e0 + tid;
         const int4 ev = ld_keep_v4(p.env4 + e, keep);
         EnvS& es = envs[tid];
-        es.t = ev.x; es.t_start = ev.y; es.ep_count = ev.z;
+        es.t = ev.x; es.t_start = ev.y; es.ep_count = ev.z; es.k_done = ev.w;
         const int t_fin = ev.y + p.L;
         int fl = 0;
         if (!p.auto_reset && ev.x >= t_fin) fl |= EF_FROZEN;   // episode over and not reset by the caller
@@ -745,7 +739,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
             soc = __ldcs(p.soc + i);
             hl = __ldcs(p.hl + i);
             soh = __ldcs(p.soh + i);
-            hrow = (size_t)e * p.RN + (unsigned)((p.calc_deg ? k : (k & 1)) * N + n);
+            hrow = (size_t)e * p.RN + (unsigned)((k & p.Rm) * N + n);
             sdeg = __ldcs(p.hist + hrow);
             const int tr = (!p.auto_reset && k >= p.L) ? min(t, p.T - 1) : min(t + 1, p.T - 1);   // frozen: row t
             rec = load_rec_keep(&p.ev_rec[(size_t)tr * N + n], keep);
@@ -775,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
 
                 __stcs(p.soc + i, soc);
                 __stcs(p.hl + i, hl);
-                const size_t hnext = p.calc_deg ? hrow + N : (hrow - (size_t)(k & 1) * N + (size_t)((k + 1) & 1) * N);
+                const size_t hnext = hrow - (size_t)((k & p.Rm) * N) + (size_t)(((k + 1) & p.Rm) * N);
                 __stcs(p.hist + hnext, sdeg);                                   // log_soc, :655-656
             } else if (p.charge_log) {
                 p.charge_log[i] = 0;                                            // frozen env: nothing flows
@@ -855,11 +849,9 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
                 p.env_f64[(size_t)EF_LAST_EP_RETURN * p.E + e] = ep_ret;
             }
             p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
-            st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, 0), keep);
-            const int wf = ((es.flags & EF_TRIGGER) ? WL_TRIGGER : 0) | ((es.flags & EF_RESET) ? WL_RESET : 0);
-            if (wf) {   // the post kernel evaluates the degradation first and resets afterwards, like the reference
-                wl_push(p, e, wf);
-            }
+            st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, es.k_done), keep);
+            const int wf = wl_flags(p, es.flags, es.t - es.t_start, es.k_done);
+            if (wf) wl_push(p, e, wf);   // the post kernel evaluates the degradation first and resets afterwards, like the reference
         }
         p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
         p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
@@ -894,6 +886,7 @@ constexpr int kPfThreads = kPfCompute + 64;     // + two epilogue warps
 struct PfEnv {   // per-env scratch of a tile (shared memory, triple buffered)
     int t, t_start, ep_count, flags;
     double S, F_cr, F_dr, Rfac, pv_share, gml, pvv;
+    int k_done, pad;
 };
 
 #ifndef KPFSTAGES
@@ -1102,7 +1095,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             int fl = 0;
             if (lane < B && tile < ntiles && e < p.E) {
                 PfEnv& es = reinterpret_cast<PfEnv*>(envs0 + ebuf * p.pf_envs_b)[lane];
-                es.t = envA.x; es.t_start = envA.y; es.ep_count = envA.z;
+                es.t = envA.x; es.t_start = envA.y; es.ep_count = envA.z; es.k_done = envA.w;
                 if (envA.x + 1 == envA.y + p.L) fl |= EF_DONE | EF_RESET;
                 if (((uint32_t)r3.w & TF_TRIGGER) && p.calc_deg) fl |= EF_TRIGGER;
                 if ((uint32_t)r3.w & TF_LUNCH) fl |= EF_LUNCH;
@@ -1178,11 +1171,9 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
                     p.env_f64[(size_t)EF_LAST_EP_RETURN * p.E + e] = ep_ret;
                 }
                 p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
-                st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, 0), keep);
-                const int wf = ((es.flags & EF_TRIGGER) ? WL_TRIGGER : 0) | ((es.flags & EF_RESET) ? WL_RESET : 0);
-                if (wf) {
-                    wl_push(p, e, wf);
-                }
+                st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, es.k_done), keep);
+                const int wf = wl_flags(p, es.flags, es.t - es.t_start, es.k_done);
+                if (wf) wl_push(p, e, wf);
                 p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
                 p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
                 p.env_f64[(size_t)EF_OVERLOAD * p.E + e] = overload;
@@ -1235,7 +1226,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
 #endif
 #ifndef PF_NOHIST
             cp_async8_hint(st + kPfStSdeg + j * 8,
-                           p.hist + ((size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)((p.calc_deg ? k : (k & 1)) * N)), stream);
+                           p.hist + ((size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)((k & p.Rm) * N)), stream);
 #endif
 #ifndef PF_NOREC
             cp_async16_hint(st + kPfStR0 + j * 16, rp, keep);
@@ -1305,7 +1296,7 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             if (hl != 0.f) sdeg = soc;
 #endif
             o_soc = soc; o_hl = hl; o_sdeg = sdeg;
-            o_hist = (size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)((p.calc_deg ? k + 1 : ((k + 1) & 1)) * N);
+            o_hist = (size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)(((k + 1) & p.Rm) * N);
             {
                 const int4 r1 = reinterpret_cast<const int4*>(stp + kPfStR1)[j];
                 rec.tt = __int_as_float(r1.x); rec.cl = __int_as_float(r1.y);
@@ -1365,353 +1356,14 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
     PF_FLUSH(8);
 }
 
-// ------------------------------------------------------------------------------------- persistent TMA step kernel
-// Same arithmetic as fleet_step_kernel, restructured for latency hiding and fewer per-thread instructions:
-//  * persistent CTAs (grid = #SMs x resident CTAs) loop over tiles of Bt consecutive envs;
-//  * WARP SPECIALISED: kWsCompute compute warps + one manager warp, no CTA-wide barrier in the loop.
-//    - the manager warp brings every input of a tile into a shared-memory STAGE with bulk-async copies
-//      (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP): the four contiguous [Bt*N] runs of actions / soc /
-//      hours_left / soh, and per env the previous history row, the schedule-record row ev_rec[t+1], the observation
-//      header row hdr[t+1] and step_row[t].  kWsStages stages are in flight, so the loads of the next tile overlap
-//      the arithmetic of the current one.
-//    - compute threads (one per (env, EV) slot) wait on the stage's `full` mbarrier, read their inputs from shared
-//      memory, update soc / hours_left / the history row IN PLACE in the stage, build the observation rows next to
-//      it, leave their per-vehicle reward/cashflow terms in a double-buffered contribution array and arrive on the
-//      stage's `done` mbarrier.
-//    - the manager warp, one tile behind, issues bulk stores for everything (state runs, history rows, one
-//      observation row per env to obs or — for a finished env — to terminal_obs), refills the stage as soon as the
-//      stores have read it, then does the per-env sequential sums and the env-level finalisation (reward, overload
-//      sigmoid, done, statistics, work list) while the compute warps are already on the next tile.
-// Selected by fleet_step when auto_reset is on, N is even (16-byte history rows), D % 4 == 0 and 7 <= N <= 224;
-// otherwise the generic kernel above runs.  tests/ exercise both.
-constexpr int kWsComputeWarps = 7;
-constexpr int kWsCompute = kWsComputeWarps * 32;       // 224 compute threads
-constexpr int kWsThreads = kWsCompute + 32;            // + manager warp
-constexpr int kWsStages = 2;
-
-__device__ __forceinline__ void tma_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-
-// byte offsets (all multiples of 16): input stage, output buffer, per-CTA arrays.  Computed once on the host and
-// passed in StepParams so that no thread spends instructions on it.
-inline TmaLayout tma_layout(int Bt, int N, int D, int hdr_stride) {
-    TmaLayout L;
-    const int bn = Bt * N;
-    auto a16 = [](size_t x) { return (int)((x + 15) & ~(size_t)15); };
-    int o = 0;
-    L.soc = o; o += a16((size_t)bn * 8);
-    L.soh = o; o += a16((size_t)bn * 8);
-    L.hist = o; o += a16((size_t)bn * 8);
-    L.rec = o; o += bn * 32;
-    L.row = o; o += Bt * 64;
-    L.act = o; o += a16((size_t)bn * 4);
-    L.hl = o; o += a16((size_t)bn * 4);
-    L.hdr = o; o += Bt * hdr_stride * 4;
-    L.in_bytes = a16((size_t)o);
-    o = 0;
-    L.o_soc = o; o += a16((size_t)bn * 8);
-    L.o_hist = o; o += a16((size_t)bn * 8);
-    L.o_hl = o; o += a16((size_t)bn * 4);
-    L.o_obs = o; o += a16((size_t)Bt * D * 4);
-    L.out_bytes = a16((size_t)o);
-    int c = 0;
-    L.in0 = c; c += L.in_bytes * kWsStages;
-    L.out0 = c; c += L.out_bytes * 2;
-    L.contrib_bytes = a16((size_t)kNQ * bn * 8);
-    L.contrib = c; c += 2 * L.contrib_bytes;
-    L.sums = c; c += a16((size_t)kNQ * Bt * 8);
-    L.bars = c; c += 8 * (3 * kWsStages + 4);
-    L.total = a16((size_t)c);
-    return L;
-}
-
-template <bool kNorm, bool kAux>
-__global__ void __launch_bounds__(kWsThreads, 3) fleet_step_tma_kernel(const StepParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = p.N, D = p.D, Bt = p.Bt;
-    const TmaLayout& L = p.tl;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
-    uint64_t* full = bars;                         // [kWsStages] loads of the input stage have landed
-    uint64_t* consumed = bars + kWsStages;         // [kWsStages] every compute thread has read its inputs
-    uint64_t* done = bars + 2 * kWsStages;         // [2]         outputs + contributions of the tile are written
-    uint64_t* ofree = bars + 2 * kWsStages + 2;    // [2]         the bulk stores have read the output buffer and the
-                                                   //             manager has consumed the contribution buffer
-    const int tid = threadIdx.x;
-    const int cstride = Bt * N;
-    const int ntiles = (p.E + Bt - 1) / Bt;
-    const int H = p.Ha + p.Hb;
-
-    if (tid == 0) {
-        for (int s = 0; s < kWsStages; s++) { mbar_init(&full[s], 1); mbar_init(&consumed[s], kWsCompute); }
-        for (int s = 0; s < 2; s++) { mbar_init(&done[s], kWsCompute); mbar_init(&ofree[s], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int tile0 = blockIdx.x;
-
-    if (tid >= kWsCompute) {
-        // =================================================================== manager warp
-        const int lane = tid - kWsCompute;
-        double* sums = reinterpret_cast<double*>(smem_raw + L.sums);
-        auto load_ev = [&](int tile) -> int4 {
-            const int e = tile * Bt + lane;
-            return (tile < ntiles && lane < Bt && e < p.E) ? p.env4[e] : make_int4(0, 0, 0, 0);
-        };
-        // issue every load of tile `tile` into input stage `s`; ev = env4 of env (tile*Bt + lane) for lane < nb
-        auto issue_tile = [&](int tile, int s, const int4 ev) {
-            const int e0 = tile * Bt;
-            const int nb = min(Bt, p.E - e0);
-            unsigned char* st = smem_raw + L.in0 + (size_t)s * L.in_bytes;
-            const size_t base = (size_t)e0 * N;
-            const uint32_t bn = (uint32_t)(nb * N);
-            if (lane == 0) {
-                const uint32_t bytes = bn * 24u + (uint32_t)nb * (uint32_t)(N * 8 + N * 32 + p.hdr_stride * 4 + 64);
-                mbar_arrive_expect_tx(&full[s], bytes);
-                tma_load(st + L.soc, p.soc + base, bn * 8u, &full[s]);
-                tma_load(st + L.soh, p.soh + base, bn * 8u, &full[s]);
-                tma_load(st + L.act, p.actions + base, bn * 4u, &full[s]);
-                tma_load(st + L.hl, p.hl + base, bn * 4u, &full[s]);
-            }
-            if (lane < nb) {
-                const int e = e0 + lane;
-                const int t = ev.x, k = ev.x - ev.y;
-                const int t1 = min(t + 1, p.T - 1);
-                tma_load(st + L.hist + (size_t)lane * N * 8,
-                         p.hist + (size_t)e * p.RN + (size_t)(p.calc_deg ? k : (k & 1)) * N, (uint32_t)(N * 8), &full[s]);
-                tma_load(st + L.rec + (size_t)lane * N * 32, p.ev_rec + (size_t)t1 * N, (uint32_t)(N * 32), &full[s]);
-                tma_load(st + L.hdr + (size_t)lane * p.hdr_stride * 4, p.hdr + (size_t)t1 * p.hdr_stride,
-                         (uint32_t)(p.hdr_stride * 4), &full[s]);
-                tma_load(st + L.row + (size_t)lane * 64, p.step_row + min(t, p.T - 2), 64u, &full[s]);
-            }
-        };
-        int4 ev_cur[kWsStages];
-#pragma unroll
-        for (int s = 0; s < kWsStages; s++) {
-            const int tl = tile0 + s * gridDim.x;
-            ev_cur[s] = load_ev(tl);
-            if (tl < ntiles) issue_tile(tl, s, ev_cur[s]);
-        }
-        int4 ev_next = load_ev(tile0 + kWsStages * gridDim.x);
-
-        int it = 0;
-        for (int tile = tile0; tile < ntiles; tile += gridDim.x, it++) {
-            const int s = it % kWsStages;
-            const uint32_t parity = (uint32_t)((it / kWsStages) & 1);
-            const int ob = it & 1;
-            const uint32_t oparity = (uint32_t)((it >> 1) & 1);
-            unsigned char* st = smem_raw + L.in0 + (size_t)s * L.in_bytes;
-            unsigned char* so = smem_raw + L.out0 + (size_t)ob * L.out_bytes;
-            const int e0 = tile * Bt;
-            const int nb = min(Bt, p.E - e0);
-            const int nslots = nb * N;
-            int4 ev_mine = make_int4(0, 0, 0, 0);
-#pragma unroll
-            for (int q = 0; q < kWsStages; q++) if (q == s) ev_mine = ev_cur[q];
-            const double* contrib = reinterpret_cast<const double*>(smem_raw + L.contrib + ob * L.contrib_bytes);
-
-            // what the manager needs from the input stage, before it is recycled
-            mbar_wait(&full[s], parity);
-            int fl = 0;
-            double gml = 0, pvv = 0;
-            if (lane < nb) {
-                const StepRow* s_row = reinterpret_cast<const StepRow*>(st + L.row);
-                const int t_fin = ev_mine.y + p.L;
-                if (ev_mine.x + 1 == t_fin) fl |= EF_DONE | EF_RESET;
-                if ((s_row[lane].flags_next & TF_TRIGGER) && p.calc_deg) fl |= EF_TRIGGER;
-                gml = s_row[lane].gml; pvv = s_row[lane].pvv;
-            }
-            // ---- refill the input stage with the tile kWsStages ahead as soon as every compute thread has read it
-            const int tile_n = tile + kWsStages * gridDim.x;
-            mbar_wait(&consumed[s], parity);
-            if (tile_n < ntiles) issue_tile(tile_n, s, ev_next);
-#pragma unroll
-            for (int q = 0; q < kWsStages; q++) if (q == s) ev_cur[q] = ev_next;
-            ev_next = load_ev(tile_n + gridDim.x);
-
-            // ---- bulk stores of everything the tile produced
-            mbar_wait(&done[ob], oparity);
-            if (lane == 0) {
-                const size_t base = (size_t)e0 * N;
-                tma_store(p.soc + base, so + L.o_soc, (uint32_t)(nslots * 8));
-                tma_store(p.hl + base, so + L.o_hl, (uint32_t)(nslots * 4));
-            }
-            if (lane < nb) {
-                const int e = e0 + lane;
-                const int k = ev_mine.x - ev_mine.y;
-                tma_store(p.hist + (size_t)e * p.RN + (size_t)(p.calc_deg ? k + 1 : ((k + 1) & 1)) * N,
-                          so + L.o_hist + (size_t)lane * N * 8, (uint32_t)(N * 8));
-                float* dst = (fl & EF_RESET) ? (p.terminal_obs ? p.terminal_obs + (size_t)e * D : nullptr)
-                                             : (p.obs ? p.obs + (size_t)e * D : nullptr);
-                if (dst) tma_store(dst, so + L.o_obs + (size_t)lane * D * 4, (uint32_t)(D * 4));
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-
-            // ---- P2: per-env sums with a FIXED reduction order (deterministic run to run): each lane adds the
-            // env's contributions lane, lane+32, ... in order, then a 5-step shuffle tree combines the 32 partials
-            for (int w = 0; w < kNQ * nb; w++) {
-                const int q = w / nb, bb = w - q * nb;
-                const double* c = contrib + q * cstride + bb * N;
-                double part = 0;
-                for (int nn = lane; nn < N; nn += 32) part += c[nn];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-                if (lane == 0) sums[q * Bt + bb] = part;
-            }
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ofree[ob]);    // output + contribution buffers may be overwritten again
-
-            // ---- P3: one lane per env
-            if (lane < nb) {
-                const int bb = lane, e = e0 + bb;
-                double* stt = p.stats + (size_t)(tile % kStatStripes) * FLEET_S__COUNT;
-                const double cashflow = sums[Q_CASH * Bt + bb];
-                double reward = sums[Q_REWARD * Bt + bb];
-                const double margin = gml - sums[Q_ATH * Bt + bb] * p.evse + pvv;                  // load_calculation.py:93
-                const double overload = fabs(margin < 0.0 ? margin : 0.0);
-                if (overload > 0) {
-                    const double rel = overload / p.grid + 1;                                      // fleet_environment.py:496
-                    const double pen = (rel < 1.1) ? 0.0 : -700 / (1 + exp(-15.77350877 * (rel - 1.33298382)));
-                    reward += pen * p.pen_ovl;                                                     // score_config.py:33-41
-                    atomicAdd(stt + FLEET_S_OVERLOAD_KW, overload);
-                }
-                const double soc_viol = fabs(sums[Q_MISS * Bt + bb]);
-                const double n_viol = sums[Q_NVIOL * Bt + bb];
-                const int dn = (fl & EF_DONE) ? 1 : 0;
-                const double ep_ret = p.env_f64[(size_t)EF_EP_RETURN * p.E + e] + reward;
-                atomicAdd(stt + FLEET_S_STEPS, 1.0);
-                atomicAdd(stt + FLEET_S_REWARD, reward);
-                atomicAdd(stt + FLEET_S_CASHFLOW, cashflow);
-                if (n_viol > 0) { atomicAdd(stt + FLEET_S_SOC_VIOL, soc_viol); atomicAdd(stt + FLEET_S_N_VIOL, n_viol); }
-                if (dn) {
-                    atomicAdd(stt + FLEET_S_EPISODES, 1.0);
-                    atomicAdd(stt + FLEET_S_EP_RETURN, ep_ret);
-                    p.env_f64[(size_t)EF_LAST_EP_RETURN * p.E + e] = ep_ret;
-                }
-                p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
-                p.env4[e] = make_int4(ev_mine.x + 1, ev_mine.y, ev_mine.z, 0);
-                const int wf = ((fl & EF_TRIGGER) ? WL_TRIGGER : 0) | ((fl & EF_RESET) ? WL_RESET : 0);
-                if (wf) {
-                    wl_push(p, e, wf);
-                }
-                p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
-                p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
-                p.env_f64[(size_t)EF_OVERLOAD * p.E + e] = overload;
-                p.env_f64[(size_t)EF_SOC_VIOL * p.E + e] = soc_viol;
-                if (p.reward) p.reward[e] = (float)reward;
-                if (p.done) p.done[e] = (uint8_t)dn;
-            }
-            __syncwarp();
-        }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        return;
-    }
-
-    // ======================================================================= compute warps
-    const bool have_flips = (*p.n_flips != 0);
-    int it = 0;
-    for (int tile = tile0; tile < ntiles; tile += gridDim.x, it++) {
-        const int s = it % kWsStages;
-        const uint32_t parity = (uint32_t)((it / kWsStages) & 1);
-        const int ob = it & 1;
-        const unsigned char* st = smem_raw + L.in0 + (size_t)s * L.in_bytes;
-        unsigned char* so = smem_raw + L.out0 + (size_t)ob * L.out_bytes;
-        const int e0 = tile * Bt;
-        const int nb = min(Bt, p.E - e0);
-        const int nslots = nb * N;
-        double* contrib = reinterpret_cast<double*>(smem_raw + L.contrib + ob * L.contrib_bytes);
-        float* obs_tile = reinterpret_cast<float*>(so + L.o_obs);
-
-        mbar_wait(&full[s], parity);
-
-        // ---- read every input of this thread's slot from the stage, then hand the stage back for refilling
-        const int j = tid;
-        const bool active = j < nslots;
-        int b = 0, n = 0;
-        float a32 = 0.f, hl = 0.f;
-        double soc = 0, soh = 1, sdeg = 0;
-        double eS = 0, eFcr = 0, eFdr = 0, eRfac = 0, ePv = 0;
-        uint32_t eflags_next = 0;
-        EvRec rec;
-        rec.sr = 0; rec.tl = 0; rec.there = rec.there_prev = 0; rec.pad = 0; rec.tt = rec.cl = rec.hn = rec.lax = 0;
-        if (active) {
-            b = (int)__umulhi((unsigned)j, p.n_magic);
-            n = j - b * N;
-            const StepRow* es = reinterpret_cast<const StepRow*>(st + L.row) + b;
-            eS = es->S; eFcr = es->F_cr; eFdr = es->F_dr; eRfac = es->Rfac; ePv = es->pv_share; eflags_next = es->flags_next;
-            a32 = reinterpret_cast<const float*>(st + L.act)[j];
-            soc = reinterpret_cast<const double*>(st + L.soc)[j];
-            hl = reinterpret_cast<const float*>(st + L.hl)[j];
-            soh = reinterpret_cast<const double*>(st + L.soh)[j];
-            sdeg = reinterpret_cast<const double*>(st + L.hist)[j];
-            const int4* s_rec = reinterpret_cast<const int4*>(st + L.rec);
-            const int4 v = s_rec[2 * j];
-            const float4 w4 = reinterpret_cast<const float4*>(s_rec)[2 * j + 1];
-            rec.sr = __hiloint2double(v.y, v.x); rec.tl = __int_as_float(v.z);
-            rec.there = (uint8_t)(v.w & 0xff); rec.there_prev = (uint8_t)((v.w >> 8) & 0xff);
-            rec.tt = w4.x; rec.cl = w4.y; rec.hn = w4.z; rec.lax = w4.w;
-        }
-        // time-only part of the observation: first element per thread in a register, the rest (small N) directly
-        float hv = 0.f; int hdst = -1;
-        const float* s_hdr = reinterpret_cast<const float*>(st + L.hdr);
-        if (tid < nb * H) {
-            const int bb = (H == 1) ? tid : (int)__umulhi((unsigned)tid, p.h_magic), q = tid - bb * H;
-            hv = s_hdr[bb * p.hdr_stride + q];
-            hdst = bb * D + (q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha));
-        }
-        if (it >= 2) mbar_wait(&ofree[ob], (uint32_t)(((it >> 1) - 1) & 1));   // output + contribution buffers are free
-        for (int w = kWsCompute + tid; w < nb * H; w += kWsCompute) {
-            const int bb = (H == 1) ? w : (int)__umulhi((unsigned)w, p.h_magic), q = w - bb * H;
-            obs_tile[bb * D + (q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha))] = s_hdr[bb * p.hdr_stride + q];
-        }
-        mbar_arrive(&consumed[s]);
-        if (hdst >= 0) obs_tile[hdst] = hv;
-
-        if (active) {
-            const size_t i = (size_t)e0 * N + j;
-            const bool flip = have_flips && p.tflip[i] != 0;
-            double q_rew = 0, q_cash = 0, q_ath = 0, q_miss = 0, q_nviol = 0;
-            struct { double S, F_cr, F_dr, Rfac, pv_share; int flags; } es;   // per-env factors read from the stage above
-            es.S = eS; es.F_cr = eFcr; es.F_dr = eFdr; es.Rfac = eRfac; es.pv_share = ePv;
-            es.flags = (eflags_next & TF_LUNCH) ? EF_LUNCH : 0;
-            double q_en = 0;
-            ev_slot_step(p, es, i, flip, (double)a32, soh, rec.sr, rec.tl, rec.there_prev, soc, hl, sdeg,
-                         q_rew, q_cash, q_ath, q_miss, q_nviol, q_en);
-            if (p.charge_log) p.charge_log[i] = q_en;
-
-            reinterpret_cast<double*>(so + L.o_soc)[j] = soc;
-            reinterpret_cast<float*>(so + L.o_hl)[j] = hl;
-            reinterpret_cast<double*>(so + L.o_hist)[j] = sdeg;
-            write_ev_obs<kNorm, kAux>(p, obs_tile + b * D, n, soc, hl, rec, flip);
-            contrib[Q_REWARD * cstride + j] = q_rew;
-            contrib[Q_CASH * cstride + j] = q_cash;
-            contrib[Q_ATH * cstride + j] = q_ath;
-            contrib[Q_MISS * cstride + j] = q_miss;
-            contrib[Q_NVIOL * cstride + j] = q_nviol;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (bulk stores)
-        mbar_arrive(&done[ob]);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ post kernel
-// One CTA of kPostThreads threads per work-list env (persistent loop over the list): first the daily degradation
-// (fleet_environment.py:665-673), then — if the episode finished and auto-reset is on — FleetEnv.reset
-// (:330-434), i.e. the order in which a SubprocVecEnv worker runs them.  The env's SOC history (<= L+1 rows of N
-// doubles) is first staged into shared memory with coalesced, deeply unrolled loads; each thread then streams its
-// vehicle's column through the three-point rainflow with an index stack in shared memory.
-__host__ __device__ inline size_t post_smem_bytes(int cap) {
-    // value ring [kStackS][64] f64 | records [cap][64] u32 | index ring [kStackS][64] u16 | reversal indices [cap][64] u16
-    return align16((size_t)kStackS * kPostThreads * 8 + (size_t)cap * kPostThreads * 4 + (size_t)kStackS * kPostThreads * 2 +
-                   (size_t)cap * kPostThreads * 2);
-}
-
+// One CTA of kPostThreads threads per work-list entry (persistent grid, entries fetched dynamically), one vehicle per
+// thread.  An entry is an env that, in this step,
+//   WL_TRIGGER  reached the daily evaluation (fleet_environment.py:665-673): consume the pending history samples, then
+//               RainflowSeiDegradation / EmpiricalDegradation.calculate_degradation, soh -= degradation;
+//   WL_FLUSH    is about to wrap its history ring: consume the pending samples (no evaluation);
+//   WL_RESET    finished its episode with auto-reset on: FleetEnv.reset (:330-434) AFTER the evaluation, i.e. the order in
+//               which a SubprocVecEnv worker runs them.
 // Auto-reset of one finished env by `nthr` cooperating threads (rank `tid`): FleetEnv.reset as the SubprocVecEnv
 // worker calls it right after a done step.  `ev` is the env's {t, t_start, ep_count} before the reset.
 template <bool kNorm, bool kAux>
@@ -1724,397 +1376,74 @@ __device__ __forceinline__ void post_reset_env(const StepParams& p, int e, int4 
         p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = 0;
     }
 }
-// The last CTA of a post kernel to finish clears both work lists for the next step.
+// The last CTA of a post kernel to finish clears the work list for the next step.
 __device__ __forceinline__ void post_finish_lists(const StepParams& p) {
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int d = atomicAdd(p.wl_done, 1u);
-        if (d == gridDim.x - 1) { p.wl_count[0] = 0; p.wl_count[1] = 0; p.wl_count[2] = 0; p.wl_count[3] = 0; *p.wl_done = 0; }
+        if (d == gridDim.x - 1) { p.wl_count[0] = 0; p.wl_count[1] = 0; *p.wl_done = 0; }
     }
 }
 
 template <bool kNorm, bool kAux>
 __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = p.N;
-    double* vring = reinterpret_cast<double*>(smem_raw);
-    const int cap = p.L + 2;
-    uint32_t* recs = reinterpret_cast<uint32_t*>(vring + kStackS * kPostThreads);
-    uint16_t* iring = reinterpret_cast<uint16_t*>(recs + cap * kPostThreads);
-    uint16_t* ridx = iring + kStackS * kPostThreads;
-    __shared__ double s_deg;
-    const int tid = threadIdx.x;
-    const int count = *p.wl_count;
-
-    PT_START();
-    for (int w = blockIdx.x; w < count; w += gridDim.x) {
-        const int2 ent = p.wl[w];
-        const int e = ent.x, wf = ent.y;
-        const int4 ev = p.env4[e];                      // {t (already advanced), t_start, ep_count}
-        const int len = ev.x - ev.y + 1;                // history rows 0..k+1 where k+1 = t - t_start
-        if (wf & WL_TRIGGER) {
-            if (tid == 0) s_deg = 0;
-            __syncthreads();
-            for (int n0 = 0; n0 < N; n0 += kPostThreads) {
-                const int n = n0 + tid;
-                if (n < N) {
-                    const size_t ii = (size_t)e * N + n;
-                    const double* hcol = p.hist + (size_t)e * p.R * N + n;
-                    double deg;
-                    if (p.deg_mode == FLEET_DEG_EMPIRICAL) {
-                        deg = empirical_eval(p.dt, p.evse, N, hcol, len);
-                        p.n_cycles[ii] = 0;
-                    } else {
-                        RfRing rg; rg.v = vring + tid; rg.i = iring + tid; rg.mask = kStackS - 1; rg.stride = kPostThreads;
-                        RfOut r = rainflow_pass1<true>(hcol, N, len, rg, recs + tid, ridx + tid);
-                        if (r.overflow) {   // stack deeper than the shared ring: redo with the global scratch ring
-                            RfRing gg;
-                            gg.v = p.post_scratch_v + ((size_t)blockIdx.x * p.scratch_cap) * kPostThreads + tid;
-                            gg.i = p.post_scratch_i + ((size_t)blockIdx.x * p.scratch_cap) * kPostThreads + tid;
-                            gg.mask = p.scratch_cap - 1; gg.stride = kPostThreads;
-                            r = rainflow_pass1<false>(hcol, N, len, gg, recs + tid, ridx + tid);
-                        }
-                        deg = sei_finish(p, ii, hcol, N, len, r, recs + tid);
-                    }
-                    p.last_deg[ii] = deg;
-                    p.soh[ii] = p.soh[ii] - deg;                                // :671 (battery_cap is derived, :673)
-                    if (deg != 0) atomicAdd(&s_deg, deg);
-                }
-            }
-            __syncthreads();
-            if (tid == 0 && s_deg != 0)
-                atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
-            PT_MARK(5);
-        }
-        if (wf & WL_RESET) post_reset_env<kNorm, kAux>(p, e, ev, tid, kPostThreads);
-        PT_MARK(6);
-        __syncthreads();
-    }
-    const int count_r = p.wl_count[1];
-    for (int w = blockIdx.x; w < count_r; w += gridDim.x) {
-        const int e = p.wlr[w];
-        post_reset_env<kNorm, kAux>(p, e, p.env4[e], tid, kPostThreads);
-    }
-    post_finish_lists(p);
-}
-
-// ------------------------------------------------------------------------- cooperative post kernel (default)
-// One CTA of 256 threads per degradation entry, fetched dynamically; the env's whole soc_deg history (len x N float64,
-// contiguous in HBM) is staged once in shared memory, transposed to one column per vehicle (odd pitch: conflict-free
-// both along and across columns), and every phase works on that copy:
-//   A. reversal detection, one WARP per vehicle, 32 samples per step: a sample is a reversal iff the nearest
-//      non-zero differences on either side have a negative product (rainflow.reversals skips plateaus and reports a
-//      plateau's last sample); found with ballots, compacted IN PLACE (values only: nothing downstream needs the
-//      sample indices, the cycle list is positional).
-//   B. the three-point stack, one THREAD per vehicle (inherently serial), vehicles spread over all 8 warps so that few
-//      lanes diverge together; the stack holds reversal ordinals in a full-depth shared-memory column (no overflow
-//      path), the top three values live in registers; cycles are recorded as (ordinal a, ordinal b, full) words.
-//   C. SEI stress of the new cycles (pow/exp per cycle), ALL threads: po_g threads per vehicle take the cycles
-//      round-robin; partial sums are combined in a fixed order (deterministic; differs from the sequential sum in the
-//      last bits only, inside the stated SOH tolerance).
-//   D. per-vehicle fade update, then the env's reset if it also finished.
-// Reset-only entries are taken by quarter CTAs (64 threads) afterwards.
-#ifndef KPOST2_BWARPS
-#define KPOST2_BWARPS 8
-#endif
-constexpr int kPost2Threads = 256;
-constexpr int kPost2DefaultChunks = 1;   // vehicle chunks per degradation entry (FLEETSTEP_POST_CHUNKS overrides)
-
-struct Post2Misc {   // per-chunk scalars in shared memory
-    double part[kPost2Threads];
-    double pmax[kPost2Threads];
-};
-
-template <bool kNorm, bool kAux>
-__global__ void __launch_bounds__(kPost2Threads) fleet_post2_kernel(const StepParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = p.N, LP = p.po_lp, NC = p.po_nc;
-    double* rv = reinterpret_cast<double*>(smem_raw);                      // [NC][LP] samples, then reversal values
-    uint16_t* stk = reinterpret_cast<uint16_t*>(smem_raw + p.po_stk);      // [NC][LP] stack of reversal ordinals
-    uint32_t* recs = reinterpret_cast<uint32_t*>(smem_raw + p.po_recs);    // [NC][LP] cycle records
-    Post2Misc* misc = reinterpret_cast<Post2Misc*>(smem_raw + p.po_misc);
-    int* s_m = reinterpret_cast<int*>(misc + 1);                           // [NC] cycles found
-    int* s_rfl = s_m + NC;                                                 // [NC] rainflow_length of the vehicle
-    double* s_msum = reinterpret_cast<double*>(s_rfl + NC);                // [NC] sum of cycle means (2*NC ints before it)
-    __shared__ int s_w, s_last;
+    double* sm_stack = reinterpret_cast<double*>(smem_raw);                    // [rf_S][kPostThreads]
+    double* sm_rev = sm_stack + (size_t)p.rf_S * kPostThreads;                 // [kRfBatch][kPostThreads]
+    __shared__ int s_w;
     __shared__ int2 s_ent;
     __shared__ int4 s_ev;
     __shared__ double s_deg;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int count_d = p.wl_count[0], count_r = p.wl_count[1];
-    const int nch = p.po_nch;                            // work items per entry (vehicle chunks spread over CTAs)
-    const int items = count_d * nch;
-    const double alpha_sei = 5.75E-2, beta_sei = 121, k_sigma = 1.04, sigma_ref = 0.5, k_temp = 6.93E-2,
-                 temp_ref = 25, k_dt = 4.14E-10, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
-    PT_START();
+    const int tid = threadIdx.x, N = p.N;
+    const int count = p.wl_count[0];
+    const double temp_ref = 25, k_temp = 6.93E-2;
+    const double s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
 
     // The first entry of a CTA is static (entry blockIdx.x), further ones come from a counter; thread 0 fetches the NEXT
     // entry's list record and env4 while the current one is processed, so the two dependent round trips are hidden.
     if (tid == 0) {
         s_w = blockIdx.x; s_deg = 0;
-        if (s_w < items) { s_ent = p.wl[s_w / nch]; s_ev = p.env4[s_ent.x]; }
+        if (s_w < count) { s_ent = p.wl[s_w]; s_ev = p.env4[s_ent.x]; }
     }
     for (;;) {
         __syncthreads();
         const int w = s_w;
-        if (w >= items) break;
-        const int entry = w / nch, chunk = w - entry * nch;
+        if (w >= count) break;
         const int2 ent = s_ent;
         const int e = ent.x, wf = ent.y;
-        const int4 ev = s_ev;                           // {t (already advanced), t_start, ep_count}
-        const int len = ev.x - ev.y + 1;                // history rows 0..k+1 where k+1 = t - t_start
+        const int4 ev = s_ev;                           // {t (already advanced), t_start, ep_count, k_done}
+        const int k_now = ev.x - ev.y;                  // newest history sample (samples 0..k_now exist)
         int w_next = 0;
         int2 ent_next = make_int2(0, 0);
         int4 ev_next = make_int4(0, 0, 0, 0);
         if (tid == 0) {
-            w_next = atomicAdd(p.wl_count + 2, 1) + (int)gridDim.x;
-            if (w_next < items) { ent_next = p.wl[w_next / nch]; ev_next = p.env4[ent_next.x]; }
+            w_next = atomicAdd(p.wl_count + 1, 1) + (int)gridDim.x;
+            if (w_next < count) { ent_next = p.wl[w_next]; ev_next = p.env4[ent_next.x]; }
         }
-        const double* hbase = p.hist + (size_t)e * p.R * N;
-
-        if (p.deg_mode == FLEET_DEG_EMPIRICAL) {           // (one item per entry in this mode)
-            for (int n = tid; n < N; n += kPost2Threads) {
+        if (p.rf_on && (wf & (WL_TRIGGER | WL_FLUSH))) {
+            for (int n = tid; n < N; n += kPostThreads) {
+                const double deg = rf_vehicle(p, e, n, ev.w, k_now, (wf & WL_TRIGGER) != 0, s_temp, sm_stack + tid, sm_rev + tid);
+                if (deg != 0) atomicAdd(&s_deg, deg);
+            }
+        } else if (wf & WL_TRIGGER) {                   // EmpiricalDegradation: the last two samples only
+            const double* hbase = p.hist + (size_t)e * p.RN;
+            for (int n = tid; n < N; n += kPostThreads) {
                 const size_t ii = (size_t)e * N + n;
-                const double deg = empirical_eval(p.dt, p.evse, N, hbase + n, len);
+                double deg = 0;
+                if (k_now >= 1) deg = empirical_eval(p.dt, p.evse, hbase[(size_t)((k_now - 1) & p.Rm) * N + n], hbase[(size_t)(k_now & p.Rm) * N + n]);
                 p.n_cycles[ii] = 0;
                 p.last_deg[ii] = deg;
                 p.soh[ii] = p.soh[ii] - deg;
                 if (deg != 0) atomicAdd(&s_deg, deg);
             }
-        } else {
-            for (int n0 = chunk * NC; n0 < min(N, (chunk + 1) * NC); n0 += NC) {   // this item's vehicles (one pass)
-                const int nc = min(NC, N - n0);
-                // ---- stage the chunk: coalesced along vehicles in HBM, one column per vehicle in shared memory;
-                // 8-byte cp.async copies, all in flight at once (one HBM round trip for the whole history)
-                for (int r = warp; r < len; r += kPost2Threads / 32) {
-                    const double* src = hbase + (size_t)r * N + n0;
-                    for (int c = lane; c < nc; c += 32) cp_async8(rv + c * LP + r, src + c);
-                }
-                // per-vehicle degradation state, needed at the end: fetched under the staging latency
-                double st_fd = 0, st_life = 0, st_soh = 0;
-                int st_rfl = 0;
-                if (tid < nc) {
-                    const size_t ii = (size_t)e * N + n0 + tid;
-                    st_fd = p.fd_cyc[ii]; st_life = p.life[ii]; st_soh = p.soh[ii]; st_rfl = p.rf_len[ii];
-                    s_rfl[tid] = st_rfl;
-                }
-                cp_async_wait_all();
-                __syncthreads();
-                PT_MARK(0);
-
-                // ---- A + B: warp `warp` owns vehicles [warp*cpw, warp*cpw+cpw) of the chunk
-                const int cpw = (nc + 7) >> 3;
-                int my_nr = 0;                                       // lane j keeps the count of the warp's j-th vehicle
-                for (int j = 0; j < cpw; j++) {
-                    const int c = warp * cpw + j;
-                    if (c >= nc) break;                              // warp-uniform
-                    double* col = rv + c * LP;
-                    int nr = 1;                                      // yield (0, x0): col[0] stays where it is
-                    if (len >= 3) {
-                        const double x_end = col[len - 1];
-                        double carry_d = col[1] - col[0];            // d_last before the loop (may be 0)
-                        for (int q0 = 1; q0 <= len - 2; q0 += 32) {
-                            const int q = q0 + lane;
-                            const bool valid = q <= len - 2;
-                            const double xa = valid ? col[q] : 0.0, xb = valid ? col[q + 1] : 0.0;
-                            const double d = xb - xa;
-                            const bool nz = valid && (xb != xa);
-                            const unsigned nzmask = __ballot_sync(0xffffffffu, nz);
-                            if (nzmask == 0) continue;               // 32 equal samples (vehicle away / idle): nothing happens
-                            const unsigned lower = nzmask & ((1u << lane) - 1u);
-                            const int src = lower ? 31 - __clz(lower) : 0;
-                            const double d_lo = __shfl_sync(0xffffffffu, d, src);
-                            const double d_prev = lower ? d_lo : carry_d;
-                            const bool rev = nz && (d_prev * d < 0);
-                            const unsigned revmask = __ballot_sync(0xffffffffu, rev);
-                            const int top = nzmask ? 31 - __clz(nzmask) : 0;
-                            const double d_top = __shfl_sync(0xffffffffu, d, top);
-                            if (nzmask) carry_d = d_top;
-                            // the ballots above are the barrier between this step's reads and its in-place writes
-                            // (positions < q0 + 32; the next step reads from q0 + 32 on)
-                            if (rev) col[nr + __popc(revmask & ((1u << lane) - 1u))] = xa;
-                            nr += __popc(revmask);
-                        }
-                        if (lane == 0) col[nr] = x_end;              // the last sample closes the series
-                        nr++;
-                    }
-                    if (lane == j) my_nr = nr;
-                }
-#if KPOST2_BWARPS == 8
-                __syncwarp();
-                PT_MARK(1);
-                if (lane < cpw && warp * cpw + lane < nc) {
-                    const int c = warp * cpw + lane;
-#else
-                // phase B on fewer warps (more lanes each): fewer warps compete for issue slots with serial code
-                if (lane < cpw && warp * cpw + lane < nc) s_m[warp * cpw + lane] = my_nr;
-                __syncthreads();
-                PT_MARK(1);
-                const int cpb = (nc + KPOST2_BWARPS - 1) / KPOST2_BWARPS;
-                if (warp < KPOST2_BWARPS && lane < cpb && warp * cpb + lane < nc) {
-                    const int c = warp * cpb + lane;
-                    my_nr = s_m[c];
-#endif
-                    const double* col = rv + c * LP;
-                    uint16_t* st = stk + c * LP;
-                    uint32_t* rc = recs + c * LP;
-                    const int nr = (len >= 2) ? my_nr : 0;
-                    int lo = 0, hi = 0, m = 0;
-                    double mean_sum = 0;
-                    double v1 = 0, v2 = 0, v3 = 0;                   // values of the top three stack entries (v3 = top)
-                    int o1 = 0, o2 = 0, o3 = 0;                      // their ordinals in the reversal list
-#define RF2_EMIT(oa, xa, ob, xb_, full)                                                       \
-    do {                                                                                      \
-        mean_sum += 0.5 * ((xa) + (xb_));                                                     \
-        rc[m] = (uint32_t)(oa) | ((uint32_t)(ob) << 15) | ((uint32_t)(full) << 30);           \
-        m++;                                                                                  \
-    } while (0)
-                    if (nr >= 2) {
-                        for (int r0 = 0; r0 < nr; r0 += 4) {
-                            double vb[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) vb[u] = col[min(r0 + u, nr - 1)];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const int r = r0 + u;
-                                if (r < nr) {
-                                    st[hi] = (uint16_t)r; hi++;
-                                    v1 = v2; o1 = o2; v2 = v3; o2 = o3; v3 = vb[u]; o3 = r;
-                                    while (hi - lo >= 3) {
-                                        const double X = fabs(v3 - v2), Y = fabs(v2 - v1);
-                                        if (X < Y) break;
-                                        if (hi - lo == 3) { RF2_EMIT(o1, v1, o2, v2, 0); lo++; }
-                                        else {
-                                            RF2_EMIT(o1, v1, o2, v2, 1);
-                                            hi -= 2;
-                                            st[hi - 1] = (uint16_t)o3;
-                                            o2 = st[hi - 2]; v2 = col[o2];
-                                            if (hi - lo >= 3) { o1 = st[hi - 3]; v1 = col[o1]; }
-                                        }
-                                    }
-                                }
-                            }
-                        }
-                        for (int k = lo; k + 1 < hi; k++) {
-                            const int oa = st[k], ob = st[k + 1];
-                            RF2_EMIT(oa, col[oa], ob, col[ob], 0);
-                        }
-                    }
-#undef RF2_EMIT
-                    s_m[c] = m;
-                    s_msum[c] = mean_sum;
-                }
-                __syncthreads();
-                PT_MARK(2);
-
-                // ---- C: stress of the cycles in the positional slice [rainflow_length-1 : m-1]  (:146)
-                const double s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
-                {
-                    const int G = p.po_g;
-                    const int c = tid / G, sub = tid - c * G;
-                    double fs = 0, mx = 0;
-                    if (c < nc) {
-                        const int m = s_m[c], rfl = s_rfl[c];
-                        if (m > rfl) {
-                            const double* col = rv + c * LP;
-                            const uint32_t* rc = recs + c * LP;
-                            for (int j = rfl - 1 + sub; j < m - 1; j += G) {
-                                const uint32_t rec = rc[j];
-                                const double xa = col[rec & 0x7fffu], xb = col[(rec >> 15) & 0x7fffu];
-                                const double range = fabs(xa - xb), mean = 0.5 * (xa + xb);
-                                double eff = range * ((rec >> 30) ? 1.0 : 0.5);                        // :170
-                                eff = eff < 0 ? 0 : (eff > 1 ? 1 : eff);
-                                const double s_dod = 1.0 / (kd1 * pow(eff, kd2) + kd3);                // :68
-                                const double s_soc = exp(k_sigma * (mean - sigma_ref));                // :70
-                                fs += s_dod * s_soc * s_temp;                                          // :77-79
-                                if (range > mx) mx = range;
-                            }
-                        }
-                    }
-                    misc->part[tid] = fs;
-                    misc->pmax[tid] = mx;
-                }
-                __syncthreads();
-                PT_MARK(3);
-
-                // ---- D: capacity fade of each vehicle (rainflow_sei_degradation.py:128-206); thread c = vehicle c
-                {
-                    double deg = 0;
-                    if (tid < nc) {
-                        const int c = tid;
-                        const size_t ii = (size_t)e * N + n0 + c;
-                        const int m = s_m[c], rfl = st_rfl;
-                        const int G = p.po_g;
-                        p.n_cycles[ii] = m;
-                        if (m > rfl) {                                                                     // :143
-                            double fsum = 0, max_dod = 0;
-                            for (int g = 0; g < G; g++) {
-                                fsum += misc->part[c * G + g];
-                                max_dod = fmax(max_dod, misc->pmax[c * G + g]);
-                            }
-                            const double battery_age = (double)(len - 1) * p.dt * 3600;                    // :138
-                            const double mean_soc_cal = s_msum[c] / (double)m;                             // :140
-                            if (max_dod > 5) atomicOr(p.err_flags, 4u);                                    // :164-167
-                            const double fd_cal = (k_dt * battery_age) * exp(k_sigma * (mean_soc_cal - sigma_ref)) * s_temp;  // :81-83
-                            const double fd_cyc = st_fd + fsum;                                            // :174
-                            p.fd_cyc[ii] = fd_cyc;
-                            const double fd = fd_cyc + fd_cal;
-                            const double l_old = st_life;
-                            double new_l;
-                            if (p.init_soh == 1.0) {
-                                new_l = 1 - alpha_sei * exp(-beta_sei * fd) - (1 - alpha_sei) * exp(-fd);  // :85-86
-                                if (new_l < 0) atomicOr(p.err_flags, 2u);                                  // :179-180
-                            } else {
-                                new_l = 1 - (1 - l_old) * exp(-fd);                                        // :89,186
-                            }
-                            deg = new_l - l_old;                                                           // :189
-                            p.life[ii] = new_l;                                                            // :192
-                            p.rf_len[ii] = m;                                                              // :195
-                        }
-                        p.last_deg[ii] = deg;
-                        p.soh[ii] = st_soh - deg;                                                          // :671
-                    }
-                    if (warp * 32 < nc) {                            // warp-uniform: fixed-order tree, one atomic per warp
-#pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) deg += __shfl_xor_sync(0xffffffffu, deg, off);
-                        if (lane == 0 && deg != 0) atomicAdd(&s_deg, deg);
-                    }
-                }
-                __syncthreads();                                     // the chunk's shared memory is reused
-                PT_MARK(4);
-            }
         }
         __syncthreads();
         if (tid == 0 && s_deg != 0)
             atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
-        if (wf & WL_RESET) {       // the env also finished: the CTA that completes its last chunk resets it
-            if (tid == 0) {
-                __threadfence();
-                s_last = (nch == 1) || (atomicAdd(&p.wl_chunk_cnt[entry], 1) == nch - 1);
-                if (s_last && nch > 1) p.wl_chunk_cnt[entry] = 0;
-            }
-            __syncthreads();
-            if (s_last) { __threadfence(); post_reset_env<kNorm, kAux>(p, e, ev, tid, kPost2Threads); }
-        }
-        __syncthreads();                                             // everybody has read s_w / s_ent / s_ev / s_deg
+        if (wf & WL_RESET) post_reset_env<kNorm, kAux>(p, e, ev, tid, kPostThreads);
+        else if (tid == 0 && p.rf_on) p.env4[e] = make_int4(ev.x, ev.y, ev.z, k_now);   // samples up to k_now are consumed
+        __syncthreads();                                 // everybody has read s_w / s_ent / s_ev / s_deg
         if (tid == 0) { s_w = w_next; s_ent = ent_next; s_ev = ev_next; s_deg = 0; }
-        PT_MARK(5);
-    }
-
-    // ---- reset-only entries: a quarter CTA (64 threads) per env
-    {
-        const int grp = tid >> 6, gt = tid & 63;
-        for (;;) {
-            __syncthreads();
-            if (tid == 0) s_w = atomicAdd(p.wl_count + 3, 4);
-            __syncthreads();
-            const int w = s_w + grp;
-            if (s_w >= count_r) break;
-            if (w < count_r) {
-                const int e = p.wlr[w];
-                post_reset_env<kNorm, kAux>(p, e, p.env4[e], gt, 64);
-            }
-        }
     }
     post_finish_lists(p);
 }
@@ -2153,6 +1482,7 @@ __global__ void init_state_kernel(StepParams p) {
         p.soc[i] = 0; p.hl[i] = 0; p.soh[i] = p.init_soh;
         p.rf_len[i] = 1; p.fd_cyc[i] = 0; p.life[i] = 1 - p.init_soh; p.n_cycles[i] = 0; p.last_deg[i] = 0;
         p.tflip[i] = 0;
+        if (p.rf_on) { p.rf_dc[i] = 1u; p.rf_acc[i] = make_double2(0.0, 0.0); p.rf_ext[i] = -1; }
     }
     if (i < (size_t)p.E) p.env4[i] = make_int4(0, 0, 0, 0);
 }
@@ -2214,7 +1544,7 @@ __global__ void gather_field_kernel(StepParams p, int field, void* dst) {
                 const int e = (int)(i / p.N), n = (int)(i - (size_t)e * p.N);
                 const int4 ev = p.env4[e];
                 const int k = ev.x - ev.y;
-                ((double*)dst)[i] = p.hist[((size_t)e * p.R + (k % p.R)) * p.N + n];
+                ((double*)dst)[i] = p.hist[((size_t)e * p.R + (k & p.Rm)) * p.N + n];
             }
             break;
         case FLEET_F_TARGET_SOC:
@@ -2264,11 +1594,9 @@ struct FleetHandle {
     int64_t bytes = 0;
     int64_t launches = 0;
     std::string err;
-    size_t smem_step = 0, smem_post = 0, smem_tma = 0, smem_pf = 0;
+    size_t smem_step = 0, smem_post = 0, smem_pf = 0;
     int grid_pf = 0, use_pf = 0;
-    int grid = 0, grid_post = 0, need_post = 0, num_sms = 0, grid_tma = 0, use_tma = 0;
-    int use_post2 = 0, grid_post2 = 0;
-    size_t smem_post2 = 0;
+    int grid = 0, grid_post = 0, need_post = 0, num_sms = 0;
     int max_smem_optin = 0;
     double* charge_log_buf = nullptr;   // fleet_enable_charge_log
     int host_zerocopy = 1;              // fleet_step_host: use page-locked host buffers in place (FLEETSTEP_HOST_ZEROCOPY)
@@ -2352,17 +1680,9 @@ StepKernel pick_pf(const FleetHandle* h, bool log) {
     if (h->c.normalize) return h->c.aux ? fleet_step_pf_kernel<true, true, false> : fleet_step_pf_kernel<true, false, false>;
     return h->c.aux ? fleet_step_pf_kernel<false, true, false> : fleet_step_pf_kernel<false, false, false>;
 }
-StepKernel pick_tma(const FleetHandle* h) {
-    if (h->c.normalize) return h->c.aux ? fleet_step_tma_kernel<true, true> : fleet_step_tma_kernel<true, false>;
-    return h->c.aux ? fleet_step_tma_kernel<false, true> : fleet_step_tma_kernel<false, false>;
-}
 StepKernel pick_post(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_post_kernel<true, true> : fleet_post_kernel<true, false>;
     return h->c.aux ? fleet_post_kernel<false, true> : fleet_post_kernel<false, false>;
-}
-StepKernel pick_post2(const FleetHandle* h) {
-    if (h->c.normalize) return h->c.aux ? fleet_post2_kernel<true, true> : fleet_post2_kernel<true, false>;
-    return h->c.aux ? fleet_post2_kernel<false, true> : fleet_post2_kernel<false, false>;
 }
 StepKernel pick_reset(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_reset_kernel<true, true> : fleet_reset_kernel<true, false>;
@@ -2370,10 +1690,6 @@ StepKernel pick_reset(const FleetHandle* h) {
 }
 
 }  // namespace
-
-static void fleet_launch_tma(FleetHandle* h, const StepParams& p, cudaStream_t stream) {
-    pick_tma(h)<<<h->grid_tma, kWsThreads, h->smem_tma, stream>>>(p);
-}
 
 extern "C" {
 
@@ -2399,7 +1715,7 @@ int fleet_enable_charge_log(FleetHandle* h, int32_t enable) {
 
 const char* fleet_step_kernel_name(const FleetHandle* h) {
     if (!h) return "";
-    return h->use_tma ? "fleet_step_tma_kernel" : (h->use_pf ? "fleet_step_pf_kernel" : "fleet_step_kernel");
+    return h->use_pf ? "fleet_step_pf_kernel" : "fleet_step_kernel";
 }
 
 int fleet_set_timing(FleetHandle* h, int32_t enable) {
@@ -2440,14 +1756,6 @@ int32_t fleet_debug_pf_clk(unsigned long long* out, int32_t reset) {
     return 0;
 }
 #endif
-#ifdef POST_TIMING
-int32_t fleet_debug_post_clk(unsigned long long* out, int32_t reset) {
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, g_post_clk, sizeof(unsigned long long) * 16);
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_post_clk, z, sizeof(z)); }
-    return 0;
-}
-#endif
 int64_t fleet_device_bytes(const FleetHandle* h) { return h ? h->bytes : 0; }
 
 int fleet_destroy(FleetHandle* h) {
@@ -2480,7 +1788,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     if (c.include_pv && !tb->pv) return fail(h, FLEET_E_INVALID, "include_pv set but pv table is NULL");
     if (c.steps_per_hour < 1 || c.episode_steps < 1) return fail(h, FLEET_E_INVALID, "steps_per_hour and episode_steps must be >= 1");
     if ((double)(float)c.dt != c.dt) return fail(h, FLEET_E_INVALID, "dt is not exactly representable in float32 (hours_left is kept in float32)");
-    if (c.episode_steps + 1 > 65535) return fail(h, FLEET_E_INVALID, "episode longer than 65535 steps is not supported yet");
+    if (c.episode_steps + 1 > 65535) return fail(h, FLEET_E_INVALID, "episodes longer than 65534 steps are not supported (16-bit cycle counters)");
 
     h->c = c; h->device = device; h->E = num_envs; h->N = c.num_evs; h->T = c.table_len;
     const int E = h->E, N = h->N, T = h->T;
@@ -2611,8 +1919,32 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     CUDA_TRY(h, cudaMemcpy(d_rows, rows.data(), rows.size() * sizeof(StepRow), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(d_hdr, hdr.data(), hdr.size() * sizeof(float), cudaMemcpyHostToDevice));
 
-    const int R = c.calc_degradation ? c.episode_steps + 1 : 2;
+    // History ring and incremental rainflow geometry.  Samples are only needed until the post kernel has consumed them
+    // (at the daily trigger, or when the ring is about to wrap), so R rows suffice for any episode length.
+    bool any_trigger = false;
+    for (int t = 0; t < T; t++) any_trigger = any_trigger || (rows[t].flags & TF_TRIGGER);
+    const bool rf_on = c.calc_degradation && c.deg_mode == FLEET_DEG_SEI && any_trigger;   // (no 14:45 row, e.g. 1-h grids: never evaluated)
+    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return (v && *v) ? atoi(v) : dflt; };
+    int R = 2;
+    if (rf_on) {
+        int want = c.rf_ring_rows > 0 ? c.rf_ring_rows : env_int("FLEETSTEP_RF_RING", 32);
+        if (want < 4) want = 4;
+        while (R < want) R <<= 1;                                                          // power of two: row = k & (R-1)
+    }
+    int rfS = 0, rfX = 0, rfP = 0;
     const size_t EN = (size_t)E * N;
+    if (rf_on) {
+        rfS = c.rf_stack_depth > 0 ? c.rf_stack_depth : env_int("FLEETSTEP_RF_STACK", 12);
+        if (rfS < 2) rfS = 2;
+        if (rfS > c.episode_steps + 1) rfS = c.episode_steps + 1;                          // a stack can never be deeper than the log
+        if (rfS < 2) rfS = 2;
+        if (rfS > 256) return fail(h, FLEET_E_INVALID, "rf_stack_depth > 256 is not supported (shared-memory stack copy)");
+        rfX = env_int("FLEETSTEP_RF_EXT", 52);
+        if (rfS + rfX > c.episode_steps + 1) rfX = c.episode_steps + 1 - rfS;
+        if (rfX < 0) rfX = 0;
+        rfP = rfX > 0 ? env_int("FLEETSTEP_RF_EXT_SLOTS", (int)(EN / 128 < 64 ? 64 : (EN / 128 > (1u << 20) ? (1u << 20) : EN / 128))) : 0;
+        if (EN >= 0x7fffffffull) return fail(h, FLEET_E_INVALID, "num_envs * num_evs must be below 2^31");
+    }
     if ((rc = dev_alloc(h, &p.env4, (size_t)E))) return rc;
     if ((rc = dev_alloc(h, &p.soc, EN))) return rc;
     if ((rc = dev_alloc(h, &p.hl, EN))) return rc;
@@ -2629,12 +1961,20 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     if ((rc = dev_alloc(h, &p.stats, (size_t)kStatStripes * FLEET_S__COUNT))) return rc;
     if ((rc = dev_alloc(h, &p.err_flags, (size_t)4))) return rc;
     if ((rc = dev_alloc(h, &p.wl, (size_t)E))) return rc;
-    if ((rc = dev_alloc(h, &p.wlr, (size_t)E))) return rc;
-    if ((rc = dev_alloc(h, &p.wl_chunk_cnt, (size_t)E))) return rc;
+    if (rf_on) {
+        if ((rc = dev_alloc(h, &p.rf_stack, EN * (size_t)rfS))) return rc;
+        if ((rc = dev_alloc(h, &p.rf_dc, EN))) return rc;
+        if ((rc = dev_alloc(h, &p.rf_acc, EN))) return rc;
+        if ((rc = dev_alloc(h, &p.rf_ext, EN))) return rc;
+        if ((rc = dev_alloc(h, &p.ext_owner, (size_t)(rfP > 0 ? rfP : 1)))) return rc;
+        if ((rc = dev_alloc(h, &p.ext_val, (size_t)(rfP > 0 ? rfP : 1) * (size_t)(rfX > 0 ? rfX : 1), false))) return rc;
+        CUDA_TRY(h, cudaMemset(p.ext_owner, 0xff, sizeof(int) * (size_t)(rfP > 0 ? rfP : 1)));
+    }
     if ((rc = dev_alloc(h, &p.wl_count, (size_t)4))) return rc;
     if ((rc = dev_alloc(h, &p.wl_done, (size_t)4))) return rc;
 
-    p.E = E; p.N = N; p.T = T; p.R = R; p.L = c.episode_steps; p.D = h->D; p.Ha = Ha; p.Hb = Hb; p.hdr_stride = hdr_stride;
+    p.rf_on = rf_on ? 1 : 0; p.rf_S = rfS; p.rf_X = rfX; p.rf_P = rfP;
+    p.E = E; p.N = N; p.T = T; p.R = R; p.Rm = R - 1; p.L = c.episode_steps; p.D = h->D; p.Ha = Ha; p.Hb = Hb; p.hdr_stride = hdr_stride;
     p.B = N >= kThreads ? 1 : kThreads / N;
     p.RN = (unsigned long long)R * (unsigned long long)N;
     p.is_ct = c.is_caretaker; p.calc_deg = c.calc_degradation; p.deg_mode = c.deg_mode; p.carry = c.carry_degradation_state;
@@ -2676,78 +2016,19 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
                  h->D, h->max_smem_optin);
         return fail(h, FLEET_E_INVALID, buf);
     }
-    // post kernel: stack rings + one 32-bit record per rainflow cycle (at most L+1 cycles per vehicle)
-    const int cap = c.episode_steps + 2;
-    if (cap > 32767) return fail(h, FLEET_E_INVALID, "episodes longer than 32765 steps are not supported (15-bit sample indices)");
-    size_t smp = post_smem_bytes(cap);
-    if (!(c.calc_degradation && c.deg_mode == FLEET_DEG_SEI)) smp = 16;
-    // the thread-per-vehicle kernel keeps one record per cycle for 64 vehicles in shared memory: too much for very long
-    // episodes, where only the cooperative kernel (which splits the vehicles into chunks) is available
-    const bool v1_ok = (int64_t)smp <= (int64_t)h->max_smem_optin;
-    h->smem_post = smp;
+    // post kernel: one CTA of kPostThreads threads per work-list env; shared memory = the vehicles' stack copies + the
+    // per-batch reversal lists
     h->num_sms = prop.multiProcessorCount;
     h->need_post = (c.calc_degradation || c.auto_reset) ? 1 : 0;
-    if (v1_ok) {
+    h->smem_post = align16((size_t)(rfS + kRfBatch) * kPostThreads * 8);
+    if ((int64_t)h->smem_post > (int64_t)h->max_smem_optin) return fail(h, FLEET_E_INVALID, "rf_stack_depth does not fit the post kernel's shared memory");
+    {
         int per_sm = 1;
-        CUDA_TRY(h, cudaFuncSetAttribute(pick_post(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post(h), kPostThreads, smp));
+        CUDA_TRY(h, cudaFuncSetAttribute(pick_post(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post(h), kPostThreads, h->smem_post));
         if (per_sm < 1) per_sm = 1;
         const int64_t g = (int64_t)h->num_sms * per_sm;
         h->grid_post = (int)(g < E ? g : E);
-    }
-    if (v1_ok && c.calc_degradation && c.deg_mode == FLEET_DEG_SEI) {
-        int sc = 64;
-        while (sc < cap) sc <<= 1;
-        p.scratch_cap = sc;
-        if ((rc = dev_alloc(h, &p.post_scratch_v, (size_t)h->grid_post * sc * kPostThreads, false))) return rc;
-        if ((rc = dev_alloc(h, &p.post_scratch_i, (size_t)h->grid_post * sc * kPostThreads, false))) return rc;
-    }
-    // cooperative post kernel (default): the env's history staged in shared memory, NC vehicles at a time
-    {
-        const char* force = getenv("FLEETSTEP_POST");     // "v1": the thread-per-vehicle kernel
-        const int R = c.episode_steps + 1;
-        const int LP = R | 1;                             // odd column pitch
-        const size_t per_vehicle = (size_t)LP * 14 + 16;  // values 8 + ordinals 2 + records 4 per row; 16 B of scalars
-        const size_t fixed = sizeof(Post2Misc) + 64;
-        auto fit = [&](size_t budget) { return budget > fixed ? (int64_t)((budget - fixed) / per_vehicle) : 0; };
-        int64_t nc = fit((size_t)(h->max_smem_optin + 1024) / 3 - 1024 - 1024);   // three CTAs per SM
-        if (nc < (N < 8 ? N : 8)) nc = fit((size_t)h->max_smem_optin);
-        if (nc > N) nc = N;
-        if (nc > kPost2Threads) nc = kPost2Threads;
-        // An entry's vehicles are split into chunks that different CTAs process concurrently: smaller CTAs' worth of
-        // shared memory -> more resident work items per SM, and the per-item latency (staging, reversal detection,
-        // stress) shrinks with the chunk; the serial three-point stack of the slowest vehicle stays the critical path.
-        {
-            const char* ck = getenv("FLEETSTEP_POST_CHUNKS");
-            int want = ck ? atoi(ck) : kPost2DefaultChunks;
-            if (want < 1) want = 1;
-            const int64_t per = (N + want - 1) / want;
-            if (per >= 1 && per < nc) nc = per;
-        }
-        const bool sei = c.calc_degradation && c.deg_mode == FLEET_DEG_SEI;
-        if ((!force || strcmp(force, "v1") != 0) && h->need_post && (nc >= 1 || !sei)) {
-            if (!sei) nc = 1;
-            p.po_nc = (int)nc; p.po_lp = LP; p.po_g = kPost2Threads / (int)nc;
-            p.po_nch = sei ? (int)((N + nc - 1) / nc) : 1;
-            p.po_stk = (int)align16((size_t)nc * LP * 8);
-            p.po_recs = (int)align16((size_t)p.po_stk + (size_t)nc * LP * 2);
-            p.po_misc = (int)align16((size_t)p.po_recs + (size_t)nc * LP * 4);
-            h->smem_post2 = align16((size_t)p.po_misc + sizeof(Post2Misc) + (size_t)(2 * nc + 2) * 4 + (size_t)nc * 8);
-            int per_sm = 1;
-            CUDA_TRY(h, cudaFuncSetAttribute(pick_post2(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post2));
-            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post2(h), kPost2Threads, h->smem_post2));
-            if (per_sm < 1) per_sm = 1;
-            const int64_t g = (int64_t)h->num_sms * per_sm;
-            const int64_t max_items = (int64_t)E * p.po_nch;
-            h->grid_post2 = (int)(g < max_items ? g : max_items);
-            h->use_post2 = 1;
-        }
-        if (!h->use_post2 && !v1_ok && h->need_post) {
-            char buf[256];
-            snprintf(buf, sizeof buf, "a %d-step episode does not fit the post kernels' shared-memory staging (%zu bytes needed, "
-                     "the device allows %d)", c.episode_steps, smp, h->max_smem_optin);
-            return fail(h, FLEET_E_INVALID, buf);
-        }
     }
     h->smem_step = sm;
     {
@@ -2756,7 +2037,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     }
     // persistent prefetching kernel (default where applicable)
     {
-        const char* force = getenv("FLEETSTEP_KERNEL");   // "generic" / "pf" / "tma"; default: pf when applicable
+        const char* force = getenv("FLEETSTEP_KERNEL");   // "generic" / "pf"; default: pf when applicable
         const bool want = !force || strcmp(force, "pf") == 0;
         const int pfB = kPfCompute / N;
         if (want && c.auto_reset && N >= 8 && pfB >= 1 && pfB <= 32) {   // the epilogue warps use one lane per env of a tile
@@ -2791,40 +2072,6 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
         if (force && strcmp(force, "pf") == 0 && !h->use_pf)
             return fail(h, FLEET_E_INVALID, "FLEETSTEP_KERNEL=pf requested but the configuration does not qualify (needs auto_reset, 8 <= N <= 256)");
     }
-    // persistent TMA kernel: applicable when every bulk copy is 16-byte aligned and sized
-    p.Bt = 0;
-    {
-        const char* force = getenv("FLEETSTEP_KERNEL");   // "generic" (default) / "tma"
-        // the persistent TMA kernel is opt-in for now: with ~30 small bulk copies per 200-vehicle tile it is limited by
-        // the per-copy overhead of the copy engine and by the manager warp, and measured no faster than the generic kernel
-        const bool want = (force && strcmp(force, "tma") == 0);
-        if (want && c.auto_reset && (N % 2 == 0) && (h->D % 4 == 0) && N <= kWsCompute && N >= 7) {
-            const int g4 = (N % 4 == 0) ? 1 : 2;               // Bt*N*4 bytes must be a multiple of 16
-            int bt = (kWsCompute / N) / g4 * g4;
-            if (bt > 32) bt = 32 / g4 * g4;                      // one manager lane per env
-            // the last (partial) tile must also give 16-byte sized float32 runs: (E % bt) * N % 4 == 0
-            while (bt >= 1 && (((E % bt) * N) % 4) != 0) bt -= g4;
-            if (bt >= 1) {
-                const TmaLayout L = tma_layout(bt, N, h->D, hdr_stride);
-                int per_sm = 0;
-                if (L.total <= h->max_smem_optin &&
-                    cudaFuncSetAttribute(pick_tma(h), cudaFuncAttributeMaxDynamicSharedMemorySize, L.total) == cudaSuccess &&
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_tma(h), kWsThreads, (size_t)L.total) == cudaSuccess &&
-                    per_sm >= 1) {
-                    p.Bt = bt;
-                    p.tl = L;
-                    h->smem_tma = (size_t)L.total;
-                    const int ntiles = (E + bt - 1) / bt;
-                    const int g = prop.multiProcessorCount * per_sm;
-                    h->grid_tma = g < ntiles ? g : ntiles;
-                    h->use_tma = 1;
-                }
-                cudaGetLastError();
-            }
-        }
-        if (force && strcmp(force, "tma") == 0 && !h->use_tma)
-            return fail(h, FLEET_E_INVALID, "FLEETSTEP_KERNEL=tma requested but the configuration does not qualify (needs auto_reset, even 7 <= N <= 224, D % 4 == 0)");
-    }
     h->grid = (E + p.B - 1) / p.B;
     CUDA_TRY(h, cudaFuncSetAttribute(pick_step(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
 
@@ -2857,14 +2104,12 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     cudaEvent_t* tev = nullptr;
     if (h->timing && !h->tev.empty()) tev = &h->tev[(size_t)(h->tcount % kTimingRing) * 3];
     if (tev) cudaEventRecord(tev[0], (cudaStream_t)stream);
-    if (h->use_tma) fleet_launch_tma(h, p, (cudaStream_t)stream);
-    else if (h->use_pf) pick_pf(h, p.charge_log != nullptr)<<<h->grid_pf, kPfThreads, h->smem_pf, (cudaStream_t)stream>>>(p);
+    if (h->use_pf) pick_pf(h, p.charge_log != nullptr)<<<h->grid_pf, kPfThreads, h->smem_pf, (cudaStream_t)stream>>>(p);
     else pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
     h->launches++;
     if (tev) cudaEventRecord(tev[1], (cudaStream_t)stream);
     if (h->need_post) {   // daily degradation, then auto-reset, for the envs the step kernel put on the work list
-        if (h->use_post2) pick_post2(h)<<<h->grid_post2, kPost2Threads, h->smem_post2, (cudaStream_t)stream>>>(p);
-        else pick_post(h)<<<h->grid_post, kPostThreads, h->smem_post, (cudaStream_t)stream>>>(p);
+        pick_post(h)<<<h->grid_post, kPostThreads, h->smem_post, (cudaStream_t)stream>>>(p);
         h->launches++;
     }
     if (tev) { cudaEventRecord(tev[2], (cudaStream_t)stream); h->tcount++; }
@@ -3052,6 +2297,7 @@ int fleet_check_errors(FleetHandle* h, uint32_t* flags_host, void* stream) {
         if (f & 1u) m += " NaN action (reference: TypeError ev_charger.py:209)";
         if (f & 2u) m += " negative battery life (rainflow_sei_degradation.py:179-180)";
         if (f & 4u) m += " DoD > 5 (rainflow_sei_degradation.py:164-167)";
+        if (f & 8u) m += " rainflow stack capacity exceeded (raise FleetConsts.rf_stack_depth)";
         return fail(h, FLEET_E_STATE, m);
     }
     return FLEET_OK;

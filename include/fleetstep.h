@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define FLEETSTEP_ABI_VERSION 1
+#define FLEETSTEP_ABI_VERSION 2
 
 enum {
     FLEET_OK = 0,
@@ -65,6 +65,12 @@ typedef struct FleetConsts {
     int32_t auto_reset;           /* 1 = SB3 VecEnv semantics: a done env is reset inside fleet_step            */
     int32_t start_lo, start_hi;   /* inclusive start-index range used by the device RNG on auto-reset           */
                                   /* (time_picker/random_time_picker.py:25-31, eval_time_picker.py:33-39)       */
+    /* Incremental rainflow (no reference counterpart; the reference keeps the whole soc_log, log_data_deg.py:14-15):  */
+    int32_t rf_ring_rows;         /* rows of the per-env soc_deg history ring (rounded up to a power of two >= 4);    */
+                                  /* 0 = default (32).  Pending rows are consumed at the daily evaluation, or when     */
+                                  /* the ring is about to wrap                                                        */
+    int32_t rf_stack_depth;       /* rainflow stack entries kept inline per vehicle, 0 = default (12); deeper stacks   */
+                                  /* borrow an extension slot; beyond that error flag bit 3 is raised (never silent)  */
     int32_t reserved0;
     uint64_t seed;                /* keys the counter-based start-index RNG: (seed, env id, episode number)     */
 
@@ -217,7 +223,8 @@ int fleet_reset_stats(FleetHandle* h, void* stream);
 
 /* Device error flags raised by kernels since the last call (bit 0: NaN action — the reference raises TypeError
  * at ev_charger.py:209; bit 1: negative battery life, rainflow_sei_degradation.py:179-180; bit 2: DoD > 5,
- * :164-167).  Synchronises the stream.  Returns FLEET_E_STATE if any bit is set. */
+ * :164-167; bit 3: a vehicle's rainflow stack outgrew rf_stack_depth plus its extension slot — recreate the handle
+ * with a larger rf_stack_depth).  Synchronises the stream.  Returns FLEET_E_STATE if any bit is set. */
 int fleet_check_errors(FleetHandle* h, uint32_t* flags_host, void* stream);
 
 /* Number of kernel launches issued through this handle so far (bench.py reports it as gpu_launches). */

@@ -44,8 +44,15 @@ def _draw(seed):
 def test_random_configuration(seed, monkeypatch):
     from fleetrl_b200._lib import FleetStepHandle
     monkeypatch.delenv("FLEETSTEP_KERNEL", raising=False)
-    monkeypatch.delenv("FLEETSTEP_POST", raising=False)
-    monkeypatch.delenv("FLEETSTEP_POST_CHUNKS", raising=False)
+    # odd seeds run with a tiny history ring / inline rainflow stack (ring flushes, extension slots)
+    if seed % 2:
+        monkeypatch.setenv("FLEETSTEP_RF_RING", "4" if seed % 4 == 1 else "8")
+        monkeypatch.setenv("FLEETSTEP_RF_STACK", "2" if seed % 4 == 1 else "5")
+        monkeypatch.setenv("FLEETSTEP_RF_EXT_SLOTS", "40000")      # one extension slot per vehicle is possible
+    else:
+        monkeypatch.delenv("FLEETSTEP_RF_RING", raising=False)
+        monkeypatch.delenv("FLEETSTEP_RF_STACK", raising=False)
+        monkeypatch.delenv("FLEETSTEP_RF_EXT_SLOTS", raising=False)
     cf = _draw(seed)
     N, E, over = cf["n_evs"], cf["E"], cf["over"]
     cap0 = dict(lmd=60.0, ut=50.0, ct=16.7)[cf["use_case"]]

@@ -29,41 +29,38 @@ CASES = {
     "lmd_5ev_soh09": dict(n_evs=5, days=12, use_case="lmd", E=16, steps=120, over=dict(init_soh=0.9)),
     "lmd_4ev_no_autoreset": dict(n_evs=4, days=12, use_case="lmd", E=8, steps=110, over=dict(auto_reset=0)),
     "lmd_12ev_nodeg_exact_soc": dict(n_evs=12, days=12, use_case="lmd", E=64, steps=230, over=dict(calc_degradation=0)),
-    # ten-day episodes: histories of up to 961 rows (the cooperative post kernel splits the vehicles into chunks to fit
-    # its shared-memory staging; ten daily evaluations per episode over a growing history)
+    # ten-day episodes: ten daily evaluations per episode over one persistent rainflow stack per vehicle
     "lmd_9ev_10day_episodes": dict(n_evs=9, days=30, use_case="lmd", E=3, steps=1000, episode_hours=240),
-    # configurations that qualify for the persistent TMA kernel (even N, D % 4 == 0, aligned last tile)
     "lmd_50ev_e36": dict(n_evs=50, days=8, use_case="lmd", E=36, steps=120),
     "ut_10ev_e50": dict(n_evs=10, days=10, use_case="ut", E=50, steps=210, episode_hours=48),
 }
 
 
-# all three step-kernel implementations are exercised: "pf" (persistent software-pipelined kernel, the default where
-# it applies: auto-reset, 8 <= N <= 256), "generic" (any configuration) and the opt-in persistent warp-specialised
-# TMA kernel (FLEETSTEP_KERNEL=tma; needs auto-reset, even 7 <= N <= 224, D % 4 == 0)
+# both step-kernel implementations are exercised: "pf" (persistent software-pipelined kernel, the default where it
+# applies: auto-reset, 8 <= N <= 256) and "generic" (any configuration).  "+ringR+stackS[+extX]" shrinks the history ring /
+# the inline rainflow stack so that ring flushes between evaluations and stack extension slots are exercised.
 KERNELS = ([(n, "pf") for n in sorted(CASES) if CASES[n]["n_evs"] >= 8 and CASES[n]["n_evs"] <= 256
             and CASES[n].get("over", {}).get("auto_reset", 1)]
-           + [(n, "generic") for n in sorted(CASES)] + [(n, "tma") for n in ("lmd_50ev_e36", "ut_10ev_e50")]
-           # the thread-per-vehicle post kernel (FLEETSTEP_POST=v1) that the cooperative one falls back to
-           + [(n, "generic+postv1") for n in ("lmd_50ev", "ct_20ev_two_trips", "lmd_300ev", "lmd_9ev_norm_nocarry",
-                                              "lmd_1ev")]
-           # vehicle chunks of a degradation entry spread over CTAs (FLEETSTEP_POST_CHUNKS)
-           + [(n, "pf+chunks3") for n in ("lmd_50ev", "ct_20ev_two_trips", "lmd_9ev_norm_nocarry")]
-           + [("lmd_300ev", "generic+chunks2"), ("lmd_7ev", "generic+chunks7")])
+           + [(n, "generic") for n in sorted(CASES)]
+           + [(n, "pf+ring4+stack2") for n in ("lmd_50ev", "ct_20ev_two_trips", "lmd_9ev_norm_nocarry")]
+           + [(n, "generic+ring8+stack3") for n in ("lmd_300ev", "lmd_7ev", "lmd_1ev", "lmd_5ev_soh09", "lmd_4ev_no_autoreset")]
+           + [("lmd_9ev_10day_episodes", "pf+ring16+stack4"), ("lmd_50ev", "pf+ring128+stack64")])
 
 
 @pytest.mark.parametrize("name,kernel", KERNELS)
 def test_gpu_vs_oracle(name, kernel, monkeypatch):
     from fleetrl_b200._lib import FleetStepHandle
     monkeypatch.setenv("FLEETSTEP_KERNEL", kernel.split("+")[0])
-    if kernel.endswith("+postv1"):
-        monkeypatch.setenv("FLEETSTEP_POST", "v1")
+    if "+stack" in kernel:
+        monkeypatch.setenv("FLEETSTEP_RF_EXT_SLOTS", "40000")      # tiny inline stacks: every vehicle may need an extension slot
     else:
-        monkeypatch.delenv("FLEETSTEP_POST", raising=False)
-    if "+chunks" in kernel:
-        monkeypatch.setenv("FLEETSTEP_POST_CHUNKS", kernel.split("+chunks")[1])
-    else:
-        monkeypatch.delenv("FLEETSTEP_POST_CHUNKS", raising=False)
+        monkeypatch.delenv("FLEETSTEP_RF_EXT_SLOTS", raising=False)
+    for var, key in (("FLEETSTEP_RF_RING", "ring"), ("FLEETSTEP_RF_STACK", "stack"), ("FLEETSTEP_RF_EXT", "ext")):
+        val = [t[len(key):] for t in kernel.split("+")[1:] if t.startswith(key)]
+        if val:
+            monkeypatch.setenv(var, val[0])
+        else:
+            monkeypatch.delenv(var, raising=False)
 
     cs = dict(CASES[name])
     E, steps = cs.pop("E"), cs.pop("steps")
@@ -100,8 +97,8 @@ def test_gpu_vs_oracle(name, kernel, monkeypatch):
 
     exact = ["time_idx", "finish_idx", "hours_left", "target_soc", "rf_len", "n_cycles", "ep_count"]
     # SOC / soc_deg are bit-exact for a given SOH.  Once a vehicle has been through a daily SEI evaluation its SOH agrees
-    # with the oracle to 1e-13 only (device pow/exp vs libm, and the cooperative post kernel adds a vehicle's cycle
-    # stress terms in a fixed but not sequential order), so its capacity and hence its SOC may differ in the last
+    # with the oracle to 1e-13 only (device pow/exp vs libm, and the incremental rainflow adds a vehicle's cycle
+    # stress terms in commit order, not list order), so its capacity and hence its SOC may differ in the last
     # bit: exact equality is asserted where degradation cannot interfere, the stated 1e-12 otherwise.
     soc_exact = (not consts.calc_degradation) or consts.deg_mode == 1
     n_done = 0
@@ -148,4 +145,25 @@ def test_gpu_vs_oracle(name, kernel, monkeypatch):
     for k in o_stats:
         np.testing.assert_allclose(g_stats[k], o_stats[k], rtol=1e-9, atol=1e-9, err_msg=f"stat {k}")
     assert gpu.check_errors() == 0 and orc.err_flags() == 0
+    gpu.close()
+
+
+def test_rainflow_stack_capacity_is_loud(monkeypatch):
+    """A rainflow stack that outgrows its inline entries + extension slot raises error flag bit 3 (never silent)."""
+    from fleetrl_b200._lib import FleetStepError, FleetStepHandle
+    monkeypatch.setenv("FLEETSTEP_RF_STACK", "2")
+    monkeypatch.setenv("FLEETSTEP_RF_EXT", "1")
+    tables, T = make_tables(seed=5, n_evs=8, days=6)
+    consts = make_consts(tables, T, 8)
+    gpu = FleetStepHandle(consts, tables, 32, device=0)
+    dev = gpu.device
+    obs = torch.zeros((32, gpu.D), dtype=torch.float32, device=dev)
+    rew = torch.zeros(32, dtype=torch.float32, device=dev)
+    done = torch.zeros(32, dtype=torch.uint8, device=dev)
+    gpu.reset(obs=obs)
+    rng = np.random.default_rng(0)
+    for s in range(100):
+        gpu.step(torch.from_numpy(rng.uniform(-1, 1, (32, 8)).astype(np.float32)).to(dev), obs, rew, done)
+    with pytest.raises(FleetStepError, match="rainflow stack capacity"):
+        gpu.check_errors()
     gpu.close()

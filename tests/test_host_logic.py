@@ -28,12 +28,13 @@ def test_header_symbols_exported():
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} is declared in fleetstep.h but not exported"
     lib.fleet_abi_version.restype = ctypes.c_int
-    assert lib.fleet_abi_version() == 1
+    from fleetrl_b200._abi import ABI_VERSION
+    assert lib.fleet_abi_version() == ABI_VERSION == 2
 
 
 def test_consts_struct_matches_header_size():
-    # 21 int32 (+pad) + uint64 + 31 doubles, laid out like the C struct
-    assert ctypes.sizeof(FleetConsts) == 80 + 8 + 8 * 31
+    # 22 int32 + uint64 + 31 doubles, laid out like the C struct
+    assert ctypes.sizeof(FleetConsts) == 88 + 8 + 8 * 31
 
 
 def test_config_resolution_order():
