@@ -328,14 +328,17 @@ __device__ __forceinline__ void reset_slot(const StepParams& p, int e, int n, in
 // of the stack is always the most recently yielded reversal), reversals are pushed, closed cycles are committed.
 // An evaluation then pushes the provisional end point onto a READ-ONLY view of the stack and counts the residue.
 constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one work-list env per CTA, one vehicle per thread)
-constexpr int kRfBatch = 8;        // history rows fetched per batch (independent loads in flight)
+constexpr int kRfSeg = 32;         // history rows staged in shared memory per pass
+constexpr int kRfPend = 8;         // cycles per lane waiting for their stress evaluation (drained warp-wide)
 
 // SEI stress of one cycle: rainflow_sei_degradation.py:68-79 with effective DoD = clip(range*count, 0, 1) (:170)
 __device__ __forceinline__ double sei_cycle_stress(double range, double count, double mean, double s_temp) {
     const double k_sigma = 1.04, sigma_ref = 0.5, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
     double eff = range * count;
     eff = eff < 0 ? 0 : (eff > 1 ? 1 : eff);
-    const double s_dod = 1.0 / (kd1 * pow(eff, kd2) + kd3);                    // :68  (dod == 0 -> inf -> 0)
+    // dod ** kd2 as exp(kd2 * log(dod)): a few ulp off a correctly rounded pow (|kd2 log dod| < 20), far inside the
+    // 1e-11 relative tolerance stated for fd_cyc, at a third of the instructions; dod == 0 -> exp(+inf) = inf -> 0
+    const double s_dod = 1.0 / (kd1 * exp(kd2 * log(eff)) + kd3);              // :68
     const double s_soc = exp(k_sigma * (mean - sigma_ref));                    // :70
     return s_dod * s_soc * s_temp;                                             // :77-79
 }
@@ -350,142 +353,6 @@ __device__ __noinline__ int rf_ext_alloc(const StepParams& p, size_t vid) {
         if (++q == P) q = 0;
     }
     return -1;
-}
-
-// One vehicle of a post-kernel entry: consume history samples k_done+1 .. k_now, then (evaluate) run
-// RainflowSeiDegradation.calculate_degradation.  smcol: this thread's column of the shared-memory stack copy
-// (entry s at smcol[s * kPostThreads]), revcol: its column of the per-batch reversal list.  Returns the SOH loss.
-__device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, int k_done, int k_now, bool evaluate,
-                                             double s_temp, double* __restrict__ smcol, double* __restrict__ revcol) {
-    const int N = p.N, S = p.rf_S, X = p.rf_X, Rm = p.Rm;
-    const size_t i = (size_t)e * N + n;
-    const unsigned int dc = p.rf_dc[i];
-    int depth = (int)(dc & 0xffffu), c = (int)(dc >> 16);
-    double2 acc = p.rf_acc[i];                               // x: sum of committed means, y: pending stress sum
-    int slot = p.rf_ext[i];
-    const int rfl = p.rf_len[i];
-    const double* __restrict__ hcol = p.hist + (size_t)e * p.RN + n;          // sample k at hcol[(k & Rm) * N]
-    double* __restrict__ stk = p.rf_stack + (size_t)e * S * N + n;            // entry s at stk[s * N]
-    double* ext = slot >= 0 ? p.ext_val + (size_t)slot * X : nullptr;
-    double x_cur = __ldcs(hcol + (size_t)(k_done & Rm) * N);
-    {
-        const int ds = depth < S ? depth : S;
-        for (int s = 0; s < ds; s++) smcol[s * kPostThreads] = stk[(size_t)s * N];
-    }
-    bool bad = false;
-#define RF_GET(s_) ((s_) < S ? smcol[(s_) * kPostThreads] : ext[(s_) - S])
-#define RF_SET(s_, v_) do { if ((s_) < S) smcol[(s_) * kPostThreads] = (v_); else ext[(s_) - S] = (v_); } while (0)
-    double max_dod = 0;
-    // cycle (xa, xb) with count `cnt` leaves the stack for good: list position c
-#define RF_COMMIT(xa, xb, cnt)                                                                 \
-    do {                                                                                       \
-        const double range_ = fabs((xa) - (xb)), mean_ = 0.5 * ((xa) + (xb));                  \
-        acc.x += mean_;                                                                        \
-        if (c >= rfl - 1) { acc.y += sei_cycle_stress(range_, (cnt), mean_, s_temp); max_dod = fmax(max_dod, range_); } \
-        c++;                                                                                   \
-    } while (0)
-    double dsg = x_cur - RF_GET(depth - 1);                  // sign of the last non-zero difference (0: none yet)
-    for (int r0 = k_done + 1; r0 <= k_now; r0 += kRfBatch) {
-        // rainflow.reversals over this batch of samples: values of the reversal points -> revcol
-        double xb[kRfBatch];
-#pragma unroll
-        for (int u = 0; u < kRfBatch; u++) xb[u] = __ldcs(hcol + (size_t)(min(r0 + u, k_now) & Rm) * N);
-        int nrev = 0;
-#pragma unroll
-        for (int u = 0; u < kRfBatch; u++) {
-            const double x_next = xb[u];
-            if (r0 + u <= k_now && x_next != x_cur) {
-                const double d = x_next - x_cur;
-                if ((dsg < 0 && d > 0) || (dsg > 0 && d < 0)) { revcol[nrev * kPostThreads] = x_cur; nrev++; }
-                dsg = d; x_cur = x_next;
-            }
-        }
-        // rainflow.extract_cycles: push each reversal, close cycles while the newest range is not smaller
-        for (int q = 0; q < nrev; q++) {
-            const double v = revcol[q * kPostThreads];
-            if (depth >= S && !ext) {
-                slot = (depth < S + X) ? rf_ext_alloc(p, i) : -1;
-                if (slot >= 0) ext = p.ext_val + (size_t)slot * X;
-            }
-            if (depth >= S + X || (depth >= S && !ext)) { bad = true; continue; }   // capacity exceeded: flagged below
-            RF_SET(depth, v); depth++;
-            while (depth >= 3) {
-                const double x3 = RF_GET(depth - 1), x2 = RF_GET(depth - 2), x1 = RF_GET(depth - 3);
-                if (fabs(x3 - x2) < fabs(x2 - x1)) break;
-                if (depth == 3) { RF_COMMIT(x1, x2, 0.5); RF_SET(0, x2); RF_SET(1, x3); depth = 2; }   // popleft
-                else { RF_COMMIT(x1, x2, 1.0); RF_SET(depth - 3, x3); depth -= 2; }
-            }
-        }
-    }
-    if (bad) atomicOr(p.err_flags, 8u);
-
-    double deg = 0;
-    if (evaluate) {
-        const double alpha_sei = 5.75E-2, beta_sei = 121, k_sigma = 1.04, sigma_ref = 0.5, k_dt = 4.14E-10;
-        const int len = k_now + 1;                           // samples in the reference's soc_log
-        int m = c;
-        double msum = acc.x, fs = 0;
-        if (len >= 3) {
-            // the last sample is always yielded as a (provisional) reversal: x_cur on top of a read-only view
-            // stack[lo .. h) of the committed points
-            int h = depth, lo = 0;
-#define RF_PROV(xa, xb, cnt, last_)                                                            \
-    do {                                                                                       \
-        const double range_ = fabs((xa) - (xb)), mean_ = 0.5 * ((xa) + (xb));                  \
-        msum += mean_;                                                                         \
-        if (!(last_) && m >= rfl - 1) { fs += sei_cycle_stress(range_, (cnt), mean_, s_temp); max_dod = fmax(max_dod, range_); } \
-        m++;                                                                                   \
-    } while (0)
-            while (h - lo >= 2) {
-                const double x2 = RF_GET(h - 1), x1 = RF_GET(h - 2);
-                if (fabs(x_cur - x2) < fabs(x2 - x1)) break;
-                if (h - lo == 2) { RF_PROV(x1, x2, 0.5, false); lo++; }
-                else { RF_PROV(x1, x2, 1.0, false); h -= 2; }
-            }
-            // "count the remaining ranges as one-half cycles", bottom first; the last of them is position m-1 of the
-            // list, which the slice [rainflow_length-1 : len-1] never includes
-            for (int k = lo; k + 1 < h; k++) RF_PROV(RF_GET(k), RF_GET(k + 1), 0.5, false);
-            RF_PROV(RF_GET(h - 1), x_cur, 0.5, true);
-#undef RF_PROV
-        }
-        p.n_cycles[i] = m;
-        if (m > rfl) {                                                                     // :143
-            const double fsum = acc.y + fs;                                                // np.sum over the slice, :174
-            const double battery_age = (double)(len - 1) * p.dt * 3600;                    // :138  max(End) == len-1
-            const double mean_soc_cal = msum / (double)m;                                  // :140
-            if (max_dod > 5) atomicOr(p.err_flags, 4u);                                    // :164-167
-            const double fd_cal = (k_dt * battery_age) * exp(k_sigma * (mean_soc_cal - sigma_ref)) * s_temp;  // :81-83
-            const double fd_cyc = p.fd_cyc[i] + fsum;                                      // :174
-            p.fd_cyc[i] = fd_cyc;
-            const double fd = fd_cyc + fd_cal;
-            const double l_old = p.life[i];
-            double new_l;
-            if (p.init_soh == 1.0) {
-                new_l = 1 - alpha_sei * exp(-beta_sei * fd) - (1 - alpha_sei) * exp(-fd);  // :85-86
-                if (new_l < 0) atomicOr(p.err_flags, 2u);                                  // :179-180
-            } else {
-                new_l = 1 - (1 - l_old) * exp(-fd);                                        // :89,186
-            }
-            deg = new_l - l_old;                                                           // :189
-            p.life[i] = new_l;                                                             // :192
-            p.rf_len[i] = m;                                                               // :195
-            acc.y = 0;                       // committed cycles below position m-1 can never be in a later slice
-        }
-        p.last_deg[i] = deg;
-        p.soh[i] = p.soh[i] - deg;                                                         // :671 (battery_cap is derived, :673)
-    }
-#undef RF_COMMIT
-    {
-        const int ds = depth < S ? depth : S;
-        for (int s = 0; s < ds; s++) stk[(size_t)s * N] = smcol[s * kPostThreads];
-    }
-#undef RF_GET
-#undef RF_SET
-    if (slot >= 0 && depth <= S) { atomicExch(&p.ext_owner[slot], -1); slot = -1; }
-    p.rf_dc[i] = (unsigned int)depth | ((unsigned int)c << 16);
-    p.rf_acc[i] = acc;
-    p.rf_ext[i] = slot;
-    return deg;
 }
 
 // EmpiricalDegradation.calculate_degradation for one vehicle (empirical_degradation.py:60-94).
@@ -528,6 +395,269 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
+}
+
+// RainflowSeiDegradation.calculate_degradation once the cycle list is known (rainflow_sei_degradation.py:128-206):
+// m cycles in the list, msum = sum of their means, fsum = stress of the slice [rainflow_length-1 : m-1].  Updates
+// fd_cyc / l / rainflow_length / soh of vehicle i and returns the SOH loss.
+__device__ __forceinline__ double sei_fade_update(const StepParams& p, size_t i, int len, int m, int rfl, double msum,
+                                                  double fsum, bool big, double s_temp, bool& consumed) {
+    const double alpha_sei = 5.75E-2, beta_sei = 121, k_sigma = 1.04, sigma_ref = 0.5, k_dt = 4.14E-10;
+    double deg = 0;
+    consumed = false;
+    p.n_cycles[i] = m;
+    if (m > rfl) {                                                                     // :143
+        const double battery_age = (double)(len - 1) * p.dt * 3600;                    // :138  max(End) == len-1
+        const double mean_soc_cal = msum / (double)m;                                  // :140
+        if (big) atomicOr(p.err_flags, 4u);                                            // :164-167
+        const double fd_cal = (k_dt * battery_age) * exp(k_sigma * (mean_soc_cal - sigma_ref)) * s_temp;  // :81-83
+        const double fd_cyc = p.fd_cyc[i] + fsum;                                      // :174
+        p.fd_cyc[i] = fd_cyc;
+        const double fd = fd_cyc + fd_cal;
+        const double l_old = p.life[i];
+        double new_l;
+        if (p.init_soh == 1.0) {
+            new_l = 1 - alpha_sei * exp(-beta_sei * fd) - (1 - alpha_sei) * exp(-fd);  // :85-86
+            if (new_l < 0) atomicOr(p.err_flags, 2u);                                  // :179-180
+        } else {
+            new_l = 1 - (1 - l_old) * exp(-fd);                                        // :89,186
+        }
+        deg = new_l - l_old;                                                           // :189
+        p.life[i] = new_l;                                                             // :192
+        p.rf_len[i] = m;                                                               // :195
+        consumed = true;
+    }
+    p.last_deg[i] = deg;
+    p.soh[i] = p.soh[i] - deg;                                                         // :671 (battery_cap is derived, :673)
+    return deg;
+}
+
+// GENERAL (slow) path for one vehicle: plain serial code straight on the vehicle's stack storage in HBM (inline entries +
+// extension slot), any depth up to S + X.  Taken by the few vehicles whose stack is, or becomes, deeper than the
+// shared-memory copy of the fast path below.  Same arithmetic, same order of the cycle list.
+__device__ __noinline__ double rf_vehicle_slow(const StepParams& p, int e, int n, int k_done, int k_now, bool evaluate,
+                                               double s_temp) {
+    const int N = p.N, S = p.rf_S, X = p.rf_X, Rm = p.Rm;
+    const size_t i = (size_t)e * N + n;
+    const unsigned int dc = p.rf_dc[i];
+    int depth = (int)(dc & 0xffffu), c = (int)(dc >> 16);
+    double2 acc = p.rf_acc[i];
+    int slot = p.rf_ext[i];
+    const int rfl = p.rf_len[i];
+    const double* hcol = p.hist + (size_t)e * p.RN + n;
+    double* stk = p.rf_stack + (size_t)e * S * N + n;
+    double* ext = slot >= 0 ? p.ext_val + (size_t)slot * X : nullptr;
+#define RF_GET(s_) ((s_) < S ? stk[(size_t)(s_) * N] : ext[(s_) - S])
+#define RF_PUT(s_, v_) do { if ((s_) < S) stk[(size_t)(s_) * N] = (v_); else ext[(s_) - S] = (v_); } while (0)
+    bool bad = false, big = false;
+    double x_cur = hcol[(size_t)(k_done & Rm) * N];
+    double dsg = x_cur - RF_GET(depth - 1);
+    for (int r = k_done + 1; r <= k_now; r++) {
+        const double x_next = hcol[(size_t)(r & Rm) * N];
+        if (x_next == x_cur) continue;
+        const double d = x_next - x_cur;
+        if ((dsg < 0 && d > 0) || (dsg > 0 && d < 0)) {      // x_cur is a reversal: push it
+            if (depth >= S && !ext) {
+                slot = (depth < S + X) ? rf_ext_alloc(p, i) : -1;
+                if (slot >= 0) ext = p.ext_val + (size_t)slot * X;
+            }
+            if (depth >= S + X || (depth >= S && !ext)) bad = true;               // capacity exceeded: dropped, flagged
+            else {
+                RF_PUT(depth, x_cur); depth++;
+                while (depth >= 3) {
+                    const double x3 = RF_GET(depth - 1), x2 = RF_GET(depth - 2), x1 = RF_GET(depth - 3);
+                    if (fabs(x3 - x2) < fabs(x2 - x1)) break;
+                    const double range = fabs(x1 - x2), mean = 0.5 * (x1 + x2);
+                    const bool half = depth == 3;
+                    acc.x += mean;
+                    if (c >= rfl - 1) { acc.y += sei_cycle_stress(range, half ? 0.5 : 1.0, mean, s_temp); big = big || range > 5; }
+                    c++;
+                    if (half) { RF_PUT(0, x2); RF_PUT(1, x3); depth = 2; }        // popleft
+                    else { RF_PUT(depth - 3, x3); depth -= 2; }
+                }
+            }
+        }
+        dsg = d; x_cur = x_next;
+    }
+    if (bad) atomicOr(p.err_flags, 8u);
+    double deg = 0;
+    if (evaluate) {
+        const int len = k_now + 1;
+        int m = c, h = depth, lo = 0;
+        double msum = acc.x, fs = 0;
+        if (len >= 3) {
+            auto prov = [&](double xa, double xb, double cnt, bool last) {
+                const double range = fabs(xa - xb), mean = 0.5 * (xa + xb);
+                msum += mean;
+                if (!last && m >= rfl - 1) { fs += sei_cycle_stress(range, cnt, mean, s_temp); big = big || range > 5; }
+                m++;
+            };
+            while (h - lo >= 2) {
+                const double x2 = RF_GET(h - 1), x1 = RF_GET(h - 2);
+                if (fabs(x_cur - x2) < fabs(x2 - x1)) break;
+                if (h - lo == 2) { prov(x1, x2, 0.5, false); lo++; }
+                else { prov(x1, x2, 1.0, false); h -= 2; }
+            }
+            for (int k = lo; k + 1 < h; k++) prov(RF_GET(k), RF_GET(k + 1), 0.5, false);
+            prov(RF_GET(h - 1), x_cur, 0.5, true);
+        }
+        bool consumed;
+        deg = sei_fade_update(p, i, len, m, rfl, msum, acc.y + fs, big, s_temp, consumed);
+        if (consumed) acc.y = 0;
+    }
+#undef RF_GET
+#undef RF_PUT
+    if (slot >= 0 && depth <= S) { atomicExch(&p.ext_owner[slot], -1); slot = -1; }
+    p.rf_dc[i] = (unsigned int)depth | ((unsigned int)c << 16);
+    p.rf_acc[i] = acc;
+    p.rf_ext[i] = slot;
+    return deg;
+}
+
+// FAST path, one vehicle per thread of a post-kernel entry, WARP-SYNCHRONOUS (all 32 lanes call it; `active` = the lane
+// has a vehicle): consume history samples k_done+1 .. k_now, then (evaluate) run calculate_degradation.
+//   smcol   this thread's column of the stack copy: entry s at smcol[s * kPostThreads], s < S (a vehicle whose stack is
+//           or gets deeper leaves for rf_vehicle_slow with its HBM state untouched); the top two entries are carried in
+//           registers (t1 = top, t2 = below)
+//   rowcol  its column of the staged history rows (compacted in place to the reversal values), pendcol its column of
+//           the pending-stress buffer
+// The vehicles of a warp have different numbers of reversals and closures.  To keep the lanes together the three-point
+// stack is cut into micro-operations and every loop iteration performs one per lane: try to place the next reversal,
+// which either lands on the stack (or closes a half cycle) and is consumed, or closes one full cycle and stays.  The
+// log/exp of the SEI stress model never run inside that loop: cycles that need them are buffered per lane and drained by
+// the whole warp.  Returns the SOH loss (0 unless evaluated).
+__device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, bool active, int k_done, int k_now,
+                                             bool evaluate, double s_temp, double* __restrict__ smcol,
+                                             double* __restrict__ rowcol, double2* __restrict__ pendcol) {
+    const unsigned full = 0xffffffffu;
+    const int N = p.N, S = p.rf_S, Rm = p.Rm;
+    const size_t i = (size_t)e * N + (active ? n : 0);
+    const double* __restrict__ hcol = p.hist + (size_t)e * p.RN + (active ? n : 0);   // sample k at hcol[(k & Rm) * N]
+    double* __restrict__ stk = p.rf_stack + (size_t)e * S * N + (active ? n : 0);     // entry s at stk[s * N]
+    int depth = 1, c = 0, rfl = 1;
+    double2 acc = make_double2(0.0, 0.0);                    // x: sum of committed means, y: pending stress sum
+    double x_cur = 0;
+    bool slow = false;                                       // this lane's vehicle takes the general path
+    if (active) {
+        const unsigned int dc = p.rf_dc[i];
+        depth = (int)(dc & 0xffffu); c = (int)(dc >> 16);
+        acc = p.rf_acc[i];
+        rfl = p.rf_len[i];
+        x_cur = __ldcs(hcol + (size_t)(k_done & Rm) * N);
+        slow = depth > S;
+        const int ds = slow ? 0 : depth;
+        for (int s = 0; s < ds; s++) smcol[s * kPostThreads] = stk[(size_t)s * N];
+    }
+    bool live = active && !slow;
+    double t1 = 0, t2 = 0;
+    if (live) { t1 = smcol[(depth - 1) * kPostThreads]; t2 = smcol[max(depth - 2, 0) * kPostThreads]; }
+    double dsg = x_cur - t1;                                 // sign of the last non-zero difference (0: none yet)
+    bool big = false;
+    int np = 0;                                              // buffered cycles
+    // cycle (xa, xb) with count cnt at list position pos_: buffered for the stress evaluation if the slice can contain it
+#define RF_CYCLE(xa, xb, cnt, pos_, want_)                                                     \
+    do {                                                                                       \
+        const double range_ = fabs((xa) - (xb)), mean_ = 0.5 * ((xa) + (xb));                  \
+        msum_ += mean_;                                                                        \
+        if ((want_) && (pos_) >= rfl - 1) { pendcol[np * kPostThreads] = make_double2(range_ * (cnt), mean_); np++; big = big || range_ > 5; } \
+    } while (0)
+#define RF_DRAIN(target_)                                                                      \
+    do {                                                                                       \
+        while (__any_sync(full, np > 0)) {                                                     \
+            if (np > 0) { np--; const double2 q_ = pendcol[np * kPostThreads]; (target_) += sei_cycle_stress(q_.x, 1.0, q_.y, s_temp); } \
+        }                                                                                      \
+    } while (0)
+
+    // ---- committed part: rainflow.reversals + extract_cycles over the pending samples
+    {
+        double& msum_ = acc.x;
+        for (int k0 = k_done + 1; k0 <= k_now; k0 += kRfSeg) {
+            const int nrows = min(kRfSeg, k_now - k0 + 1);
+            if (live)
+                for (int r = 0; r < nrows; r++) cp_async8(rowcol + r * kPostThreads, hcol + (size_t)((k0 + r) & Rm) * N);
+            cp_async_wait_all();                             // each thread reads back only its own copies: no barrier
+            // reversals(): lock-step over the rows, the reversal values are compacted in place (write index <= read index)
+            int nrev = 0;
+            if (live) {
+                for (int r = 0; r < nrows; r++) {
+                    const double x_next = rowcol[r * kPostThreads];
+                    if (x_next != x_cur) {
+                        const double d = x_next - x_cur;
+                        if ((dsg < 0 && d > 0) || (dsg > 0 && d < 0)) { rowcol[nrev * kPostThreads] = x_cur; nrev++; }
+                        dsg = d; x_cur = x_next;
+                    }
+                }
+            }
+            // extract_cycles(): one micro-operation per lane and iteration
+            int q = 0;
+            while (__any_sync(full, q < nrev)) {
+                if (q < nrev) {
+                    const double v = rowcol[q * kPostThreads];
+                    if (depth < 2) { t2 = t1; t1 = v; depth = 2; q++; }
+                    else if (fabs(v - t1) < fabs(t1 - t2)) {                           // X < Y: read the next point
+                        if (depth >= S) { slow = true; live = false; nrev = 0; }       // outgrows the copy: general path
+                        else { smcol[(depth - 2) * kPostThreads] = t2; t2 = t1; t1 = v; depth++; q++; }
+                    } else if (depth == 2) {                 // Y contains the starting point: half cycle, popleft
+                        RF_CYCLE(t2, t1, 0.5, c, true); c++;
+                        t2 = t1; t1 = v; q++;
+                    } else {                                 // full cycle: discard its peak and valley, v stays pending
+                        RF_CYCLE(t2, t1, 1.0, c, true); c++;
+                        depth -= 2;
+                        t1 = smcol[(depth - 1) * kPostThreads];
+                        t2 = smcol[max(depth - 2, 0) * kPostThreads];
+                    }
+                }
+                if (__any_sync(full, np == kRfPend)) RF_DRAIN(acc.y);
+            }
+        }
+        RF_DRAIN(acc.y);
+    }
+    // the top two entries go back to the stack copy
+    if (live) { smcol[(depth - 1) * kPostThreads] = t1; if (depth >= 2) smcol[(depth - 2) * kPostThreads] = t2; }
+
+    // ---- evaluation: the provisional end point x_cur on a READ-ONLY view stack[lo .. h) of the committed points
+    double deg = 0;
+    if (evaluate) {                                          // (uniform over the CTA)
+        const int len = k_now + 1;                           // samples in the reference's soc_log
+        int m = c, h = depth, lo = 0, k = 0;
+        double msum_ = acc.x, fs = 0;
+        int phase = (live && len >= 3) ? 0 : 2;              // 0: closures, 1: residue, 2: done
+        while (__any_sync(full, phase < 2)) {
+            if (phase == 0) {
+                bool closed = false;
+                if (h - lo >= 2) {
+                    const double x2 = smcol[(h - 1) * kPostThreads], x1 = smcol[(h - 2) * kPostThreads];
+                    if (!(fabs(x_cur - x2) < fabs(x2 - x1))) {
+                        closed = true;
+                        if (h - lo == 2) { RF_CYCLE(x1, x2, 0.5, m, true); m++; lo++; }
+                        else { RF_CYCLE(x1, x2, 1.0, m, true); m++; h -= 2; }
+                    }
+                }
+                if (!closed) { phase = 1; k = lo; }
+            } else if (phase == 1) {
+                // "count the remaining ranges as one-half cycles", bottom first; the last of them is list position m-1,
+                // which the slice [rainflow_length-1 : len-1] never includes
+                if (k + 1 < h) { RF_CYCLE(smcol[k * kPostThreads], smcol[(k + 1) * kPostThreads], 0.5, m, true); m++; k++; }
+                else { RF_CYCLE(smcol[(h - 1) * kPostThreads], x_cur, 0.5, m, false); m++; phase = 2; }
+            }
+            if (__any_sync(full, np == kRfPend)) RF_DRAIN(fs);
+        }
+        RF_DRAIN(fs);
+        if (live) {
+            bool consumed;
+            deg = sei_fade_update(p, i, len, m, rfl, msum_, acc.y + fs, big, s_temp, consumed);
+            if (consumed) acc.y = 0;         // committed cycles below position m-1 can never be in a later slice
+        }
+    }
+#undef RF_CYCLE
+#undef RF_DRAIN
+    if (live) {
+        for (int s = 0; s < depth; s++) stk[(size_t)s * N] = smcol[s * kPostThreads];
+        p.rf_dc[i] = (unsigned int)depth | ((unsigned int)c << 16);
+        p.rf_acc[i] = acc;
+    }
+    if (slow) deg = rf_vehicle_slow(p, e, n, k_done, k_now, evaluate, s_temp);
+    return deg;
 }
 
 // --------------------------------------------------------------------------------------- TMA bulk store helpers
@@ -1386,10 +1516,11 @@ __device__ __forceinline__ void post_finish_lists(const StepParams& p) {
 }
 
 template <bool kNorm, bool kAux>
-__global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm_stack = reinterpret_cast<double*>(smem_raw);                    // [rf_S][kPostThreads]
-    double* sm_rev = sm_stack + (size_t)p.rf_S * kPostThreads;                 // [kRfBatch][kPostThreads]
+    double* sm_rows = sm_stack + (size_t)p.rf_S * kPostThreads;                // [kRfSeg][kPostThreads]
+    double2* sm_pend = reinterpret_cast<double2*>(sm_rows + (size_t)kRfSeg * kPostThreads);   // [kRfPend][kPostThreads]
     __shared__ int s_w;
     __shared__ int2 s_ent;
     __shared__ int4 s_ev;
@@ -1421,8 +1552,10 @@ __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const StepPara
             if (w_next < count) { ent_next = p.wl[w_next]; ev_next = p.env4[ent_next.x]; }
         }
         if (p.rf_on && (wf & (WL_TRIGGER | WL_FLUSH))) {
-            for (int n = tid; n < N; n += kPostThreads) {
-                const double deg = rf_vehicle(p, e, n, ev.w, k_now, (wf & WL_TRIGGER) != 0, s_temp, sm_stack + tid, sm_rev + tid);
+            for (int n0 = 0; n0 < N; n0 += kPostThreads) {   // (all lanes of a warp go in together)
+                const int n = n0 + tid;
+                const double deg = rf_vehicle(p, e, n, n < N, ev.w, k_now, (wf & WL_TRIGGER) != 0, s_temp, sm_stack + tid,
+                                              sm_rows + tid, sm_pend + tid);
                 if (deg != 0) atomicAdd(&s_deg, deg);
             }
         } else if (wf & WL_TRIGGER) {                   // EmpiricalDegradation: the last two samples only
@@ -2020,7 +2153,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     // per-batch reversal lists
     h->num_sms = prop.multiProcessorCount;
     h->need_post = (c.calc_degradation || c.auto_reset) ? 1 : 0;
-    h->smem_post = align16((size_t)(rfS + kRfBatch) * kPostThreads * 8);
+    h->smem_post = align16((size_t)(rfS + kRfSeg + 2 * kRfPend) * kPostThreads * 8);
     if ((int64_t)h->smem_post > (int64_t)h->max_smem_optin) return fail(h, FLEET_E_INVALID, "rf_stack_depth does not fit the post kernel's shared memory");
     {
         int per_sm = 1;

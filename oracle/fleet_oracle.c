@@ -61,6 +61,7 @@ typedef struct Oracle {
     const int32_t* next_start; /* optional injected start indices for auto-reset */
     double stats[FLEET_S__COUNT];
     uint32_t err_flags;
+    struct Pool* pool;     /* persistent worker threads of oracle_step_mt (CPU-baseline timing) */
 } Oracle;
 
 /* ------------------------------------------------------------------------------------------------ helpers */
@@ -543,8 +544,11 @@ Oracle* oracle_create(const FleetConsts* consts, const FleetTables* tb, int32_t 
     return o;
 }
 
+static void pool_destroy(struct Pool* p);
+
 void oracle_destroy(Oracle* o) {
     if (!o) return;
+    pool_destroy(o->pool);
     for (int32_t i = 0; i < o->E; i++) { free(o->envs[i].soc); free(o->envs[i].n_cycles); free(o->envs[i].hist); }
     free(o->envs);
     free((void*)o->tb.there); free((void*)o->tb.time_left); free((void*)o->tb.soc_on_return);
@@ -626,26 +630,92 @@ static void* step_range(void* arg) {
     return NULL;
 }
 
+/* Persistent worker pool: the threads are created once per Oracle and woken for every step (creating and joining
+ * them every step made the CPU-baseline numbers depend on the scheduler's mood). */
+typedef struct Pool {
+    pthread_mutex_t mu;
+    pthread_cond_t go, done_cv;
+    pthread_t* th;
+    StepJob* jobs;
+    int32_t n, generation, pending, quit;
+} Pool;
+
+typedef struct { Pool* p; int32_t k; } WorkerArg;
+
+static void* pool_worker(void* arg) {
+    WorkerArg* wa = (WorkerArg*)arg;
+    Pool* p = wa->p;
+    const int32_t k = wa->k;
+    free(wa);
+    int32_t seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&p->mu);
+        while (p->generation == seen && !p->quit) pthread_cond_wait(&p->go, &p->mu);
+        if (p->quit) { pthread_mutex_unlock(&p->mu); return NULL; }
+        seen = p->generation;
+        pthread_mutex_unlock(&p->mu);
+        step_range(&p->jobs[k]);
+        pthread_mutex_lock(&p->mu);
+        if (--p->pending == 0) pthread_cond_signal(&p->done_cv);
+        pthread_mutex_unlock(&p->mu);
+    }
+}
+
+static void pool_destroy(Pool* p) {
+    if (!p) return;
+    pthread_mutex_lock(&p->mu);
+    p->quit = 1;
+    pthread_cond_broadcast(&p->go);
+    pthread_mutex_unlock(&p->mu);
+    for (int32_t k = 1; k < p->n; k++) pthread_join(p->th[k], NULL);
+    pthread_mutex_destroy(&p->mu); pthread_cond_destroy(&p->go); pthread_cond_destroy(&p->done_cv);
+    free(p->th); free(p->jobs); free(p);
+}
+
+static Pool* pool_create(int32_t n) {
+    Pool* p = (Pool*)calloc(1, sizeof(Pool));
+    pthread_mutex_init(&p->mu, NULL); pthread_cond_init(&p->go, NULL); pthread_cond_init(&p->done_cv, NULL);
+    p->n = n;
+    p->th = (pthread_t*)calloc((size_t)n, sizeof(pthread_t));
+    p->jobs = (StepJob*)calloc((size_t)n, sizeof(StepJob));
+    for (int32_t k = 1; k < n; k++) {
+        WorkerArg* wa = (WorkerArg*)malloc(sizeof(WorkerArg));
+        wa->p = p; wa->k = k;
+        pthread_create(&p->th[k], NULL, pool_worker, wa);
+    }
+    return p;
+}
+
 /* reward64/cashflow/terminal_obs may be NULL.  n_threads > 1 splits the envs over POSIX threads (used by the
  * CPU-baseline timing only; envs are independent). */
 void oracle_step_mt(Oracle* o, const float* actions, float* obs, double* reward64, double* cashflow, uint8_t* done,
                     float* terminal_obs, int32_t n_threads) {
     if (n_threads < 1) n_threads = 1;
     if (n_threads > o->E) n_threads = o->E > 0 ? o->E : 1;
-    StepJob* jobs = (StepJob*)calloc((size_t)n_threads, sizeof(StepJob));
-    pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    if (o->pool && o->pool->n != n_threads) { pool_destroy(o->pool); o->pool = NULL; }
+    if (!o->pool) o->pool = pool_create(n_threads);
+    Pool* p = o->pool;
     for (int32_t k = 0; k < n_threads; k++) {
-        StepJob* j = &jobs[k];
+        StepJob* j = &p->jobs[k];
         j->o = o; j->lo = (int32_t)((int64_t)o->E * k / n_threads); j->hi = (int32_t)((int64_t)o->E * (k + 1) / n_threads);
         j->actions = actions; j->obs = obs; j->reward64 = reward64; j->cashflow = cashflow; j->done = done;
         j->terminal_obs = terminal_obs;
-        if (k > 0) pthread_create(&th[k], NULL, step_range, j);
     }
-    step_range(&jobs[0]);
-    for (int32_t k = 1; k < n_threads; k++) pthread_join(th[k], NULL);
+    if (n_threads > 1) {
+        pthread_mutex_lock(&p->mu);
+        p->pending = n_threads - 1;
+        p->generation++;
+        pthread_cond_broadcast(&p->go);
+        pthread_mutex_unlock(&p->mu);
+    }
+    step_range(&p->jobs[0]);
+    if (n_threads > 1) {
+        pthread_mutex_lock(&p->mu);
+        while (p->pending > 0) pthread_cond_wait(&p->done_cv, &p->mu);
+        pthread_mutex_unlock(&p->mu);
+    }
     for (int32_t k = 0; k < n_threads; k++)
-        for (int q = 0; q < FLEET_S__COUNT; q++) o->stats[q] += jobs[k].st[q];
-    free(jobs); free(th);
+        for (int q = 0; q < FLEET_S__COUNT; q++) o->stats[q] += p->jobs[k].st[q];
 }
 
 void oracle_step(Oracle* o, const float* actions, float* obs, double* reward64, double* cashflow, uint8_t* done,
