@@ -12,7 +12,7 @@ import torch
 from ._abi import ABI_VERSION, FIELDS, STATS, FleetConsts, FleetTables
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfleetstep.so")
+LIB_PATH = os.environ.get("FLEETSTEP_LIB") or os.path.join(_HERE, "libfleetstep.so")   # FLEETSTEP_LIB: diagnostic builds
 _LIB = None
 
 _TORCH_DTYPES = {np.float64: torch.float64, np.float32: torch.float32, np.int32: torch.int32, np.uint8: torch.uint8}

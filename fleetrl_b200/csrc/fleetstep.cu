@@ -116,7 +116,7 @@ struct StepParams {
     double* last_deg;         // [E][N]
     // incremental rainflow: the three-point stack of rainflow.extract_cycles persists per vehicle
     int rf_S, rf_X, rf_P;     // inline stack entries per vehicle, entries per extension slot, number of extension slots
-    double* rf_stack;         // [E][S][N] committed reversal points still on the stack (entry 0 = bottom)
+    double* rf_stack;         // [E][N][S] committed reversal points still on the stack (entry 0 = bottom)
     unsigned int* rf_dc;      // [E][N] stack depth | committed cycles of the episode << 16
     double2* rf_acc;          // [E][N] {sum of the means of the committed cycles, stress sum of those at list positions >= rainflow_length-1}
     int* rf_ext;              // [E][N] extension slot holding stack entries >= S, or -1
@@ -300,7 +300,7 @@ __device__ __forceinline__ void reset_slot(const StepParams& p, int e, int n, in
         // (the rainflow_length / fd_cyc / l members above survive unless reinit_deg)
         const int slot = p.rf_ext[i];
         if (slot >= 0) { atomicExch(&p.ext_owner[slot], -1); p.rf_ext[i] = -1; }
-        p.rf_stack[((size_t)e * p.rf_S + 0) * p.N + n] = sdeg;
+        p.rf_stack[i * (size_t)p.rf_S] = sdeg;
         p.rf_dc[i] = 1u;
         p.rf_acc[i] = make_double2(0.0, 0.0);
     }
@@ -327,9 +327,21 @@ __device__ __forceinline__ void reset_slot(const StepParams& p, int e, int n, in
 // consumed sample (the direction of the last non-zero difference is the sign of x_cur - top of stack, because the top
 // of the stack is always the most recently yielded reversal), reversals are pushed, closed cycles are committed.
 // An evaluation then pushes the provisional end point onto a READ-ONLY view of the stack and counts the residue.
+#ifdef POST_TIMING   // diagnostic build: cycles per phase of the post kernel, taken by thread 0 of every CTA (scripts/post_timing.py)
+__device__ unsigned long long g_post_clk[16];
+#define PT_START() long long _pt = clock64()
+#define PT_MARK(k) do { if (threadIdx.x == 0) { const long long _c = clock64(); atomicAdd(&g_post_clk[k], (unsigned long long)(_c - _pt)); _pt = _c; } } while (0)
+#define PT_COUNT(k, n) do { if (threadIdx.x == 0) atomicAdd(&g_post_clk[k], (unsigned long long)(n)); } while (0)
+#else
+#define PT_START() do {} while (0)
+#define PT_MARK(k) do {} while (0)
+#define PT_COUNT(k, n) do {} while (0)
+#endif
 constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one work-list env per CTA, one vehicle per thread)
-constexpr int kRfSeg = 32;         // history rows staged in shared memory per pass
-constexpr int kRfPend = 8;         // cycles per lane waiting for their stress evaluation (drained warp-wide)
+constexpr int kRfBatch = 8;        // history rows in flight per lane while scanning
+constexpr int kRfQueue = 16;       // reversal values queued per lane between two runs of the three-point stack
+constexpr int kRfPend = 8;         // cycles per lane ...
+constexpr int kRfFlat = 128;       // ... and per warp waiting for their stress evaluation (evaluated by the whole warp)
 
 // SEI stress of one cycle: rainflow_sei_degradation.py:68-79 with effective DoD = clip(range*count, 0, 1) (:170)
 __device__ __forceinline__ double sei_cycle_stress(double range, double count, double mean, double s_temp) {
@@ -445,10 +457,10 @@ __device__ __noinline__ double rf_vehicle_slow(const StepParams& p, int e, int n
     int slot = p.rf_ext[i];
     const int rfl = p.rf_len[i];
     const double* hcol = p.hist + (size_t)e * p.RN + n;
-    double* stk = p.rf_stack + (size_t)e * S * N + n;
+    double* stk = p.rf_stack + i * (size_t)S;
     double* ext = slot >= 0 ? p.ext_val + (size_t)slot * X : nullptr;
-#define RF_GET(s_) ((s_) < S ? stk[(size_t)(s_) * N] : ext[(s_) - S])
-#define RF_PUT(s_, v_) do { if ((s_) < S) stk[(size_t)(s_) * N] = (v_); else ext[(s_) - S] = (v_); } while (0)
+#define RF_GET(s_) ((s_) < S ? stk[(s_)] : ext[(s_) - S])
+#define RF_PUT(s_, v_) do { if ((s_) < S) stk[(s_)] = (v_); else ext[(s_) - S] = (v_); } while (0)
     bool bad = false, big = false;
     double x_cur = hcol[(size_t)(k_done & Rm) * N];
     double dsg = x_cur - RF_GET(depth - 1);
@@ -518,100 +530,144 @@ __device__ __noinline__ double rf_vehicle_slow(const StepParams& p, int e, int n
 // has a vehicle): consume history samples k_done+1 .. k_now, then (evaluate) run calculate_degradation.
 //   smcol   this thread's column of the stack copy: entry s at smcol[s * kPostThreads], s < S (a vehicle whose stack is
 //           or gets deeper leaves for rf_vehicle_slow with its HBM state untouched); the top two entries are carried in
-//           registers (t1 = top, t2 = below)
-//   rowcol  its column of the staged history rows (compacted in place to the reversal values), pendcol its column of
-//           the pending-stress buffer
-// The vehicles of a warp have different numbers of reversals and closures.  To keep the lanes together the three-point
-// stack is cut into micro-operations and every loop iteration performs one per lane: try to place the next reversal,
-// which either lands on the stack (or closes a half cycle) and is consumed, or closes one full cycle and stays.  The
-// log/exp of the SEI stress model never run inside that loop: cycles that need them are buffered per lane and drained by
-// the whole warp.  Returns the SOH loss (0 unless evaluated).
+//           registers (t1 = top, t2 = below) together with Y = |t1 - t2| (+inf while there is only one point)
+//   qcol    its column of the reversal queue
+//   flat / myidx   the WARP's list of cycles waiting for their SEI stress, and this lane's indices into it
+// The lanes of a warp scan the history rows in lock-step (coalesced loads, eight in flight, branch-free) and queue the
+// reversal values; whenever a queue could overflow, and at the end, the queues are emptied by the three-point stack.
+// The vehicles of a warp have different numbers of reversals and closures, so the stack is cut into micro-operations
+// and every loop iteration performs one per lane: try to place the next reversal, which either lands on the stack (or
+// closes a half cycle) and is consumed, or closes one full cycle and stays.  The log/exp of the SEI stress model never
+// run inside that loop: cycles that need them are appended to the warp's list, which all 32 lanes evaluate together
+// (one cycle per lane, whoever owns it); each owner then adds up its own results in list order (deterministic).
+// Returns the SOH loss (0 unless evaluated).
+struct RfWarpBuf {
+    double2* flat;             // [kRfFlat] {range * count, mean} -> .x replaced by the stress
+    unsigned char* myidx;      // [kRfPend][32]
+};
+
 __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, bool active, int k_done, int k_now,
                                              bool evaluate, double s_temp, double* __restrict__ smcol,
-                                             double* __restrict__ rowcol, double2* __restrict__ pendcol) {
+                                             double* __restrict__ qcol, const RfWarpBuf wb) {
     const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int N = p.N, S = p.rf_S, Rm = p.Rm;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const size_t i = (size_t)e * N + (active ? n : 0);
     const double* __restrict__ hcol = p.hist + (size_t)e * p.RN + (active ? n : 0);   // sample k at hcol[(k & Rm) * N]
-    double* __restrict__ stk = p.rf_stack + (size_t)e * S * N + (active ? n : 0);     // entry s at stk[s * N]
-    int depth = 1, c = 0, rfl = 1;
+    double* __restrict__ stk = p.rf_stack + i * (size_t)S;                            // entry s at stk[s]
+    int depth = 1, c = 0, rflm1 = 0;
     double2 acc = make_double2(0.0, 0.0);                    // x: sum of committed means, y: pending stress sum
     double x_cur = 0;
-    bool slow = false;                                       // this lane's vehicle takes the general path
-    if (active) {
+    if (active) {                                            // everything this lane needs, one round trip
         const unsigned int dc = p.rf_dc[i];
-        depth = (int)(dc & 0xffffu); c = (int)(dc >> 16);
         acc = p.rf_acc[i];
-        rfl = p.rf_len[i];
+        rflm1 = p.rf_len[i] - 1;
         x_cur = __ldcs(hcol + (size_t)(k_done & Rm) * N);
-        slow = depth > S;
-        const int ds = slow ? 0 : depth;
-        for (int s = 0; s < ds; s++) smcol[s * kPostThreads] = stk[(size_t)s * N];
+        for (int s = 0; s < S; s += 2) {                     // (S is even; entries >= depth are don't-cares)
+            const double2 v2 = *reinterpret_cast<const double2*>(stk + s);
+            smcol[s * kPostThreads] = v2.x; smcol[(s + 1) * kPostThreads] = v2.y;
+        }
+        depth = (int)(dc & 0xffffu); c = (int)(dc >> 16);
     }
+    bool slow = active && depth > S;                         // this lane's vehicle takes the general path
     bool live = active && !slow;
-    double t1 = 0, t2 = 0;
-    if (live) { t1 = smcol[(depth - 1) * kPostThreads]; t2 = smcol[max(depth - 2, 0) * kPostThreads]; }
-    double dsg = x_cur - t1;                                 // sign of the last non-zero difference (0: none yet)
+    PT_START();
+    double t1 = 0, t2 = 0, Y = inf;
+    if (live) {
+        t1 = smcol[(depth - 1) * kPostThreads];
+        if (depth >= 2) { t2 = smcol[(depth - 2) * kPostThreads]; Y = fabs(t1 - t2); }
+    }
+    double dsg = live ? x_cur - t1 : 0.0;                    // sign of the last non-zero difference (0: none yet)
     bool big = false;
-    int np = 0;                                              // buffered cycles
-    // cycle (xa, xb) with count cnt at list position pos_: buffered for the stress evaluation if the slice can contain it
-#define RF_CYCLE(xa, xb, cnt, pos_, want_)                                                     \
+    int np = 0, cnt = 0;                                     // this lane's / the warp's cycles waiting for their stress
+    bool has_item = false;
+    double item_eff = 0, item_mean = 0;
+    // (converged code) append the lanes' new cycles to the warp's list; evaluate the list when it may not take another round
+#define RF_APPEND(target_)                                                                     \
     do {                                                                                       \
-        const double range_ = fabs((xa) - (xb)), mean_ = 0.5 * ((xa) + (xb));                  \
-        msum_ += mean_;                                                                        \
-        if ((want_) && (pos_) >= rfl - 1) { pendcol[np * kPostThreads] = make_double2(range_ * (cnt), mean_); np++; big = big || range_ > 5; } \
+        const unsigned b_ = __ballot_sync(full, has_item);                                     \
+        if (b_) {                                                                              \
+            if (has_item) {                                                                    \
+                const int idx_ = cnt + __popc(b_ & lt_mask);                                   \
+                wb.flat[idx_] = make_double2(item_eff, item_mean);                             \
+                wb.myidx[np * 32 + lane] = (unsigned char)idx_; np++;                          \
+                has_item = false;                                                              \
+            }                                                                                  \
+            cnt += __popc(b_);                                                                 \
+            if (__any_sync(full, np == kRfPend) || cnt > kRfFlat - 32) RF_DRAIN(target_);      \
+        }                                                                                      \
     } while (0)
 #define RF_DRAIN(target_)                                                                      \
     do {                                                                                       \
-        while (__any_sync(full, np > 0)) {                                                     \
-            if (np > 0) { np--; const double2 q_ = pendcol[np * kPostThreads]; (target_) += sei_cycle_stress(q_.x, 1.0, q_.y, s_temp); } \
+        if (cnt > 0) {                                                                         \
+            __syncwarp();                                                                      \
+            for (int t_ = lane; t_ < cnt; t_ += 32) {                                          \
+                const double2 it_ = wb.flat[t_];                                               \
+                wb.flat[t_].x = sei_cycle_stress(it_.x, 1.0, it_.y, s_temp);                   \
+            }                                                                                  \
+            __syncwarp();                                                                      \
+            for (int k_ = 0; k_ < np; k_++) (target_) += wb.flat[wb.myidx[k_ * 32 + lane]].x;  \
+            np = 0; cnt = 0;                                                                   \
+            __syncwarp();                                                                      \
         }                                                                                      \
     } while (0)
 
     // ---- committed part: rainflow.reversals + extract_cycles over the pending samples
-    {
-        double& msum_ = acc.x;
-        for (int k0 = k_done + 1; k0 <= k_now; k0 += kRfSeg) {
-            const int nrows = min(kRfSeg, k_now - k0 + 1);
-            if (live)
-                for (int r = 0; r < nrows; r++) cp_async8(rowcol + r * kPostThreads, hcol + (size_t)((k0 + r) & Rm) * N);
-            cp_async_wait_all();                             // each thread reads back only its own copies: no barrier
-            // reversals(): lock-step over the rows, the reversal values are compacted in place (write index <= read index)
-            int nrev = 0;
-            if (live) {
-                for (int r = 0; r < nrows; r++) {
-                    const double x_next = rowcol[r * kPostThreads];
-                    if (x_next != x_cur) {
-                        const double d = x_next - x_cur;
-                        if ((dsg < 0 && d > 0) || (dsg > 0 && d < 0)) { rowcol[nrev * kPostThreads] = x_cur; nrev++; }
-                        dsg = d; x_cur = x_next;
-                    }
-                }
-            }
-            // extract_cycles(): one micro-operation per lane and iteration
+    int nq = 0;                                              // queued reversals
+    for (int r0 = k_done + 1; ; r0 += kRfBatch) {
+        const bool more = r0 <= k_now;                       // (uniform over the CTA)
+        // extract_cycles(): empty the queues when the next batch might not fit, and after the last row
+        if (__any_sync(full, more ? nq > kRfQueue - kRfBatch : nq > 0)) {
+            PT_MARK(2);
             int q = 0;
-            while (__any_sync(full, q < nrev)) {
-                if (q < nrev) {
-                    const double v = rowcol[q * kPostThreads];
-                    if (depth < 2) { t2 = t1; t1 = v; depth = 2; q++; }
-                    else if (fabs(v - t1) < fabs(t1 - t2)) {                           // X < Y: read the next point
-                        if (depth >= S) { slow = true; live = false; nrev = 0; }       // outgrows the copy: general path
-                        else { smcol[(depth - 2) * kPostThreads] = t2; t2 = t1; t1 = v; depth++; q++; }
-                    } else if (depth == 2) {                 // Y contains the starting point: half cycle, popleft
-                        RF_CYCLE(t2, t1, 0.5, c, true); c++;
+            while (__any_sync(full, q < nq)) {
+                if (q < nq) {
+                    const double v = qcol[q * kPostThreads];
+                    const bool lt = fabs(v - t1) < Y;                                  // X < Y: read the next point
+                    if (!lt) {
+                        // close the cycle (t2, t1): a half cycle if Y contains the starting point (popleft), else a full one
+                        const double mean = 0.5 * (t2 + t1);
+                        acc.x += mean;
+                        if (c >= rflm1) { has_item = true; item_eff = depth == 2 ? 0.5 * Y : Y; item_mean = mean; big = big || Y > 5; }
+                        c++;
+                    }
+                    if (lt && depth >= S) { slow = true; live = false; nq = 0; }       // outgrows the copy: general path
+                    else if (lt || depth == 2) {
+                        if (lt) { smcol[max(depth - 2, 0) * kPostThreads] = t2; depth++; }
                         t2 = t1; t1 = v; q++;
+                        Y = fabs(t1 - t2);
                     } else {                                 // full cycle: discard its peak and valley, v stays pending
-                        RF_CYCLE(t2, t1, 1.0, c, true); c++;
                         depth -= 2;
                         t1 = smcol[(depth - 1) * kPostThreads];
                         t2 = smcol[max(depth - 2, 0) * kPostThreads];
+                        Y = depth >= 2 ? fabs(t1 - t2) : inf;
                     }
                 }
-                if (__any_sync(full, np == kRfPend)) RF_DRAIN(acc.y);
+                PT_COUNT(10, 1);
+                RF_APPEND(acc.y);
             }
+            nq = 0;
+            PT_MARK(3);
         }
-        RF_DRAIN(acc.y);
+        if (!more) break;
+        // reversals(): eight rows in flight, lock-step over the lanes, no branches.  Rows past k_now repeat the last
+        // sample (d == 0: nothing happens); d_last * d_next < 0 is the reference's own test.
+        double xb[kRfBatch];
+#pragma unroll
+        for (int u = 0; u < kRfBatch; u++) xb[u] = __ldcs(hcol + (size_t)(min(r0 + u, k_now) & Rm) * N);
+#pragma unroll
+        for (int u = 0; u < kRfBatch; u++) {
+            const double d = xb[u] - x_cur;
+            const bool flip = live && (dsg * d < 0);
+            if (flip) { qcol[nq * kPostThreads] = x_cur; nq++; }
+            dsg = (d != 0) ? d : dsg;
+            x_cur = live ? xb[u] : x_cur;
+        }
     }
+    RF_DRAIN(acc.y);
+    PT_MARK(4);
     // the top two entries go back to the stack copy
     if (live) { smcol[(depth - 1) * kPostThreads] = t1; if (depth >= 2) smcol[(depth - 2) * kPostThreads] = t2; }
 
@@ -620,43 +676,58 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
     if (evaluate) {                                          // (uniform over the CTA)
         const int len = k_now + 1;                           // samples in the reference's soc_log
         int m = c, h = depth, lo = 0, k = 0;
-        double msum_ = acc.x, fs = 0;
+        double msum = acc.x, fs = 0;
         int phase = (live && len >= 3) ? 0 : 2;              // 0: closures, 1: residue, 2: done
         while (__any_sync(full, phase < 2)) {
             if (phase == 0) {
                 bool closed = false;
                 if (h - lo >= 2) {
                     const double x2 = smcol[(h - 1) * kPostThreads], x1 = smcol[(h - 2) * kPostThreads];
-                    if (!(fabs(x_cur - x2) < fabs(x2 - x1))) {
+                    const double yy = fabs(x2 - x1);
+                    if (!(fabs(x_cur - x2) < yy)) {
                         closed = true;
-                        if (h - lo == 2) { RF_CYCLE(x1, x2, 0.5, m, true); m++; lo++; }
-                        else { RF_CYCLE(x1, x2, 1.0, m, true); m++; h -= 2; }
+                        const double mean = 0.5 * (x1 + x2);
+                        msum += mean;
+                        if (m >= rflm1) { has_item = true; item_eff = h - lo == 2 ? 0.5 * yy : yy; item_mean = mean; big = big || yy > 5; }
+                        m++;
+                        if (h - lo == 2) lo++; else h -= 2;
                     }
                 }
                 if (!closed) { phase = 1; k = lo; }
             } else if (phase == 1) {
                 // "count the remaining ranges as one-half cycles", bottom first; the last of them is list position m-1,
                 // which the slice [rainflow_length-1 : len-1] never includes
-                if (k + 1 < h) { RF_CYCLE(smcol[k * kPostThreads], smcol[(k + 1) * kPostThreads], 0.5, m, true); m++; k++; }
-                else { RF_CYCLE(smcol[(h - 1) * kPostThreads], x_cur, 0.5, m, false); m++; phase = 2; }
+                const double xa = smcol[k * kPostThreads], xb2 = (k + 1 < h) ? smcol[(k + 1) * kPostThreads] : x_cur;
+                const double mean = 0.5 * (xa + xb2);
+                msum += mean;
+                if (k + 1 < h) {
+                    const double rg = fabs(xa - xb2);
+                    if (m >= rflm1) { has_item = true; item_eff = 0.5 * rg; item_mean = mean; big = big || rg > 5; }
+                    k++;
+                } else phase = 2;
+                m++;
             }
-            if (__any_sync(full, np == kRfPend)) RF_DRAIN(fs);
+            RF_APPEND(fs);
         }
         RF_DRAIN(fs);
         if (live) {
             bool consumed;
-            deg = sei_fade_update(p, i, len, m, rfl, msum_, acc.y + fs, big, s_temp, consumed);
+            deg = sei_fade_update(p, i, len, m, rflm1 + 1, msum, acc.y + fs, big, s_temp, consumed);
             if (consumed) acc.y = 0;         // committed cycles below position m-1 can never be in a later slice
         }
     }
-#undef RF_CYCLE
+#undef RF_APPEND
 #undef RF_DRAIN
+    PT_MARK(5);
     if (live) {
-        for (int s = 0; s < depth; s++) stk[(size_t)s * N] = smcol[s * kPostThreads];
+        for (int s = 0; s < S; s += 2)
+            *reinterpret_cast<double2*>(stk + s) = make_double2(smcol[s * kPostThreads], smcol[(s + 1) * kPostThreads]);
         p.rf_dc[i] = (unsigned int)depth | ((unsigned int)c << 16);
         p.rf_acc[i] = acc;
     }
+    PT_MARK(6);
     if (slow) deg = rf_vehicle_slow(p, e, n, k_done, k_now, evaluate, s_temp);
+    PT_MARK(7);
     return deg;
 }
 
@@ -1516,11 +1587,14 @@ __device__ __forceinline__ void post_finish_lists(const StepParams& p) {
 }
 
 template <bool kNorm, bool kAux>
-__global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(kPostThreads, 10) fleet_post_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm_stack = reinterpret_cast<double*>(smem_raw);                    // [rf_S][kPostThreads]
-    double* sm_rows = sm_stack + (size_t)p.rf_S * kPostThreads;                // [kRfSeg][kPostThreads]
-    double2* sm_pend = reinterpret_cast<double2*>(sm_rows + (size_t)kRfSeg * kPostThreads);   // [kRfPend][kPostThreads]
+    double* sm_queue = sm_stack + (size_t)p.rf_S * kPostThreads;               // [kRfQueue][kPostThreads]
+    RfWarpBuf wb;                                                              // per warp
+    wb.flat = reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * kPostThreads) + (threadIdx.x >> 5) * kRfFlat;
+    wb.myidx = reinterpret_cast<unsigned char*>(reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * kPostThreads) +
+                                                (kPostThreads / 32) * kRfFlat) + (threadIdx.x >> 5) * (kRfPend * 32);
     __shared__ int s_w;
     __shared__ int2 s_ent;
     __shared__ int4 s_ev;
@@ -1551,11 +1625,14 @@ __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const __grid_c
             w_next = atomicAdd(p.wl_count + 1, 1) + (int)gridDim.x;
             if (w_next < count) { ent_next = p.wl[w_next]; ev_next = p.env4[ent_next.x]; }
         }
+        PT_START();
+        PT_COUNT(11, 1);
         if (p.rf_on && (wf & (WL_TRIGGER | WL_FLUSH))) {
+            PT_COUNT(12, 1);
             for (int n0 = 0; n0 < N; n0 += kPostThreads) {   // (all lanes of a warp go in together)
                 const int n = n0 + tid;
                 const double deg = rf_vehicle(p, e, n, n < N, ev.w, k_now, (wf & WL_TRIGGER) != 0, s_temp, sm_stack + tid,
-                                              sm_rows + tid, sm_pend + tid);
+                                              sm_queue + tid, wb);
                 if (deg != 0) atomicAdd(&s_deg, deg);
             }
         } else if (wf & WL_TRIGGER) {                   // EmpiricalDegradation: the last two samples only
@@ -1571,11 +1648,13 @@ __global__ void __launch_bounds__(kPostThreads) fleet_post_kernel(const __grid_c
             }
         }
         __syncthreads();
+        PT_MARK(8);
         if (tid == 0 && s_deg != 0)
             atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
         if (wf & WL_RESET) post_reset_env<kNorm, kAux>(p, e, ev, tid, kPostThreads);
         else if (tid == 0 && p.rf_on) p.env4[e] = make_int4(ev.x, ev.y, ev.z, k_now);   // samples up to k_now are consumed
         __syncthreads();                                 // everybody has read s_w / s_ent / s_ev / s_deg
+        PT_MARK(9);
         if (tid == 0) { s_w = w_next; s_ent = ent_next; s_ev = ev_next; s_deg = 0; }
     }
     post_finish_lists(p);
@@ -1881,6 +1960,14 @@ int fleet_get_timing(FleetHandle* h, double* step_ms, double* post_ms, int64_t* 
     if (steps) *steps = n;
     return FLEET_OK;
 }
+#ifdef POST_TIMING
+int32_t fleet_debug_post_clk(unsigned long long* out, int32_t reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_post_clk, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_post_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif
 #ifdef PF_TIMING
 int32_t fleet_debug_pf_clk(unsigned long long* out, int32_t reset) {
     cudaDeviceSynchronize();
@@ -2071,6 +2158,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
         if (rfS < 2) rfS = 2;
         if (rfS > c.episode_steps + 1) rfS = c.episode_steps + 1;                          // a stack can never be deeper than the log
         if (rfS < 2) rfS = 2;
+        rfS += rfS & 1;                                                                    // even: 16-byte vector access
         if (rfS > 256) return fail(h, FLEET_E_INVALID, "rf_stack_depth > 256 is not supported (shared-memory stack copy)");
         rfX = env_int("FLEETSTEP_RF_EXT", 52);
         if (rfS + rfX > c.episode_steps + 1) rfX = c.episode_steps + 1 - rfS;
@@ -2153,7 +2241,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     // per-batch reversal lists
     h->num_sms = prop.multiProcessorCount;
     h->need_post = (c.calc_degradation || c.auto_reset) ? 1 : 0;
-    h->smem_post = align16((size_t)(rfS + kRfSeg + 2 * kRfPend) * kPostThreads * 8);
+    h->smem_post = align16((size_t)(rfS + kRfQueue) * kPostThreads * 8 + (size_t)(kPostThreads / 32) * (kRfFlat * 16 + kRfPend * 32));
     if ((int64_t)h->smem_post > (int64_t)h->max_smem_optin) return fail(h, FLEET_E_INVALID, "rf_stack_depth does not fit the post kernel's shared memory");
     {
         int per_sm = 1;
