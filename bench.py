@@ -69,6 +69,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-envs", type=int, default=2048)
+    ap.add_argument("--settle-episodes", type=int, default=0,
+                    help="extra untimed episodes after de-phasing (rainflow_length converges to its running maximum)")
     args = ap.parse_args()
     cf = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -304,7 +306,7 @@ def main():
     for s in range(L):
         h.step_unchecked(ptrs[s % 8], o_p, r_p, d_p, t_p, sp)
         h.reset(mask=(phase == s).to(torch.uint8), obs=obs)
-    for s in range(W):
+    for s in range(W + args.settle_episodes * L):
         h.step_unchecked(ptrs[s % 8], o_p, r_p, d_p, t_p, sp)
     torch.cuda.synchronize(dev)
     h.reset_stats()

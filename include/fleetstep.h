@@ -67,7 +67,7 @@ typedef struct FleetConsts {
                                   /* (time_picker/random_time_picker.py:25-31, eval_time_picker.py:33-39)       */
     /* Incremental rainflow (no reference counterpart; the reference keeps the whole soc_log, log_data_deg.py:14-15):  */
     int32_t rf_ring_rows;         /* rows of the per-env soc_deg history ring (rounded up to a power of two >= 4);    */
-                                  /* 0 = default (32).  Pending rows are consumed at the daily evaluation, or when     */
+                                  /* 0 = default (16).  Pending rows are consumed at the daily evaluation, or when     */
                                   /* the ring is about to wrap                                                        */
     int32_t rf_stack_depth;       /* rainflow stack entries kept inline per vehicle, 0 = default (12); deeper stacks   */
                                   /* borrow an extension slot; beyond that error flag bit 3 is raised (never silent)  */
