@@ -51,9 +51,6 @@ constexpr uint32_t TF_LUNCH = 2u;    // 11 < hour < 15                 fleet_env
 
 // per-env tile flags
 constexpr int EF_FROZEN = 1, EF_DONE = 2, EF_TRIGGER = 4, EF_LUNCH = 8, EF_RESET = 16;
-// work-list flags (see wl_push)
-constexpr int WL_TRIGGER = 1, WL_RESET = 2, WL_FLUSH = 4, WL_SLOW = 8;
-constexpr unsigned int kRfSlowBit = 0x8000u;   // rf_dc: the vehicle's pending samples wait for the general path
 
 // One (time, vehicle) schedule record, 32 bytes = one L2 sector: SOC_on_return, time_left, There at this row and
 // at the previous row, and the auxiliary observation terms of observer_bl_pv.py:85-91 for the un-raised target
@@ -120,7 +117,7 @@ struct StepParams {
     // incremental rainflow: the three-point stack of rainflow.extract_cycles persists per vehicle
     int rf_S, rf_X, rf_P;     // inline stack entries per vehicle, entries per extension slot, number of extension slots
     double* rf_stack;         // [E][N][S] committed reversal points still on the stack (entry 0 = bottom)
-    unsigned int* rf_dc;      // [E][N] stack depth (15 bits) | kRfSlowBit | committed cycles of the episode << 16
+    unsigned int* rf_dc;      // [E][N] stack depth | committed cycles of the episode << 16
     double2* rf_acc;          // [E][N] {sum of the means of the committed cycles, stress sum of those at list positions >= rainflow_length-1}
     int* rf_ext;              // [E][N] extension slot holding stack entries >= S, or -1
     int* ext_owner;           // [P] vehicle index owning the slot, or -1
@@ -129,10 +126,8 @@ struct StepParams {
     double* stats;            // [kStatStripes][FLEET_S__COUNT]
     unsigned int* err_flags;  // [1]
     const int* next_start;    // [E] or nullptr
-    int2* wl;                 // [E * (1 + chunks)] work list of the post kernel: {env, WL_* flags | chunk << 4 | k_done << 12}
-    int2* wl_rf;              // [E] work list of the rainflow kernel (same record)
-    int* wl_count;            // [4] {post entries, next post entry to fetch, rainflow entries, next rainflow item to fetch}
-    int rf_nch;               // 32-vehicle chunks per env (work items of the rainflow kernel per entry)
+    int2* wl;                 // [E] work list of the post kernel: {env, WL_* flags}
+    int* wl_count;            // [4] {entries, next entry to fetch, -, -}
     unsigned int* wl_done;    // [1]
     // persistent step kernel geometry (host-computed so that the kernel reads it from the constant bank, not registers)
     int pf_B, pf_bulk, pf_ntiles, pf_cslots, pf_cper, pf_pair;      // pf_B: envs per tile = kPfCompute / N
@@ -457,7 +452,7 @@ __device__ __noinline__ double rf_vehicle_slow(const StepParams& p, int e, int n
     const int N = p.N, S = p.rf_S, X = p.rf_X, Rm = p.Rm;
     const size_t i = (size_t)e * N + n;
     const unsigned int dc = p.rf_dc[i];
-    int depth = (int)(dc & 0x7fffu), c = (int)(dc >> 16);
+    int depth = (int)(dc & 0xffffu), c = (int)(dc >> 16);
     double2 acc = p.rf_acc[i];
     int slot = p.rf_ext[i];
     const int rfl = p.rf_len[i];
@@ -531,101 +526,101 @@ __device__ __noinline__ double rf_vehicle_slow(const StepParams& p, int e, int n
     return deg;
 }
 
-// The WARP's list of cycles waiting for their SEI stress, and each lane's indices into it.  The log/exp of the stress
-// model never run inside the divergent rainflow loops: cycles that need them are appended to the list, which all 32 lanes
-// evaluate together (one cycle per lane, whoever owns it); each owner then adds up its own results in list order
-// (deterministic).
+// FAST path, one vehicle per thread of a post-kernel entry, WARP-SYNCHRONOUS (all 32 lanes call it; `active` = the lane
+// has a vehicle): consume history samples k_done+1 .. k_now, then (evaluate) run calculate_degradation.
+//   smcol   this thread's column of the stack copy: entry s at smcol[s * kPostThreads], s < S (a vehicle whose stack is
+//           or gets deeper leaves for rf_vehicle_slow with its HBM state untouched); the top two entries are carried in
+//           registers (t1 = top, t2 = below) together with Y = |t1 - t2| (+inf while there is only one point)
+//   qcol    its column of the reversal queue
+//   flat / myidx   the WARP's list of cycles waiting for their SEI stress, and this lane's indices into it
+// The lanes of a warp scan the history rows in lock-step (coalesced loads, eight in flight, branch-free) and queue the
+// reversal values; whenever a queue could overflow, and at the end, the queues are emptied by the three-point stack.
+// The vehicles of a warp have different numbers of reversals and closures, so the stack is cut into micro-operations
+// and every loop iteration performs one per lane: try to place the next reversal, which either lands on the stack (or
+// closes a half cycle) and is consumed, or closes one full cycle and stays.  The log/exp of the SEI stress model never
+// run inside that loop: cycles that need them are appended to the warp's list, which all 32 lanes evaluate together
+// (one cycle per lane, whoever owns it); each owner then adds up its own results in list order (deterministic).
+// Returns the SOH loss (0 unless evaluated).
 struct RfWarpBuf {
     double2* flat;             // [kRfFlat] {range * count, mean} -> .x replaced by the stress
     unsigned char* myidx;      // [kRfPend][32]
 };
-struct RfPend {                // per-lane registers of the mechanism
-    int np, cnt;               // this lane's / the warp's waiting cycles
-    bool has_item;
-    double item_eff, item_mean;
-};
-__device__ __forceinline__ void rf_pend_drain(const RfWarpBuf& wb, RfPend& pd, double& target, double s_temp) {
-    const int lane = threadIdx.x & 31;
-    if (pd.cnt > 0) {                                        // (uniform over the warp)
-        __syncwarp();
-        for (int t = lane; t < pd.cnt; t += 32) {
-            const double2 it = wb.flat[t];
-            wb.flat[t].x = sei_cycle_stress(it.x, 1.0, it.y, s_temp);
-        }
-        __syncwarp();
-        for (int k = 0; k < pd.np; k++) target += wb.flat[wb.myidx[k * 32 + lane]].x;
-        pd.np = 0; pd.cnt = 0;
-        __syncwarp();
-    }
-}
-// (converged code) append the lanes' new cycles; evaluate the list when it may not take another round
-__device__ __forceinline__ void rf_pend_append(const RfWarpBuf& wb, RfPend& pd, double& target, double s_temp) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned b = __ballot_sync(full, pd.has_item);
-    if (b) {
-        if (pd.has_item) {
-            const int idx = pd.cnt + __popc(b & ((1u << lane) - 1u));
-            wb.flat[idx] = make_double2(pd.item_eff, pd.item_mean);
-            wb.myidx[pd.np * 32 + lane] = (unsigned char)idx;
-            pd.np++;
-            pd.has_item = false;
-        }
-        pd.cnt += __popc(b);
-        if (__any_sync(full, pd.np == kRfPend) || pd.cnt > kRfFlat - 32) rf_pend_drain(wb, pd, target, s_temp);
-    }
-}
 
-// FAST consumption, one vehicle per lane, WARP-SYNCHRONOUS (all 32 lanes call it; `active` = the lane has a vehicle):
-// consume history samples k_done+1 .. k_now of vehicle (e, n).
-//   smcol   this lane's column of the stack copy: entry s at smcol[s * 32], s < S; the top two entries are carried in
-//           registers (t1 = top, t2 = below) together with Y = |t1 - t2| (+inf while there is only one point)
-//   qcol    its column of the reversal queue
-// A vehicle whose stack is, or gets, deeper than S keeps its HBM state untouched, gets kRfSlowBit and is finished by
-// rf_vehicle_slow in the post kernel; the function returns true for such a lane.
-// The lanes scan the history rows in lock-step (coalesced loads, eight in flight, branch-free) and queue the reversal
-// values; whenever a queue could overflow, and at the end, the queues are emptied by the three-point stack.  The vehicles
-// of a warp have different numbers of reversals and closures, so the stack is cut into micro-operations and every loop
-// iteration performs one per lane: try to place the next reversal, which either lands on the stack (or closes a half
-// cycle) and is consumed, or closes one full cycle and stays.
-__device__ __forceinline__ bool rf_consume(const StepParams& p, int e, int n, bool active, int k_done, int k_now, double s_temp,
-                                           double* __restrict__ smcol, double* __restrict__ qcol, const RfWarpBuf wb) {
+__device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, bool active, int k_done, int k_now,
+                                             bool evaluate, double s_temp, double* __restrict__ smcol,
+                                             double* __restrict__ qcol, const RfWarpBuf wb) {
     const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int N = p.N, S = p.rf_S, Rm = p.Rm;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const size_t i = (size_t)e * N + (active ? n : 0);
     const double* __restrict__ hcol = p.hist + (size_t)e * p.RN + (active ? n : 0);   // sample k at hcol[(k & Rm) * N]
     double* __restrict__ stk = p.rf_stack + i * (size_t)S;                            // entry s at stk[s]
-    unsigned int dc = 1u;
-    int rflm1 = 0;
+    int depth = 1, c = 0, rflm1 = 0;
     double2 acc = make_double2(0.0, 0.0);                    // x: sum of committed means, y: pending stress sum
     double x_cur = 0;
     if (active) {                                            // everything this lane needs, one round trip
-        dc = p.rf_dc[i];
+        const unsigned int dc = p.rf_dc[i];
         acc = p.rf_acc[i];
         rflm1 = p.rf_len[i] - 1;
         x_cur = __ldcs(hcol + (size_t)(k_done & Rm) * N);
         for (int s = 0; s < S; s += 2) {                     // (S is even; entries >= depth are don't-cares)
             const double2 v2 = *reinterpret_cast<const double2*>(stk + s);
-            smcol[s * 32] = v2.x; smcol[(s + 1) * 32] = v2.y;
+            smcol[s * kPostThreads] = v2.x; smcol[(s + 1) * kPostThreads] = v2.y;
         }
+        depth = (int)(dc & 0xffffu); c = (int)(dc >> 16);
     }
-    int depth = (int)(dc & 0x7fffu), c = (int)(dc >> 16);
     bool slow = active && depth > S;                         // this lane's vehicle takes the general path
     bool live = active && !slow;
+    PT_START();
     double t1 = 0, t2 = 0, Y = inf;
     if (live) {
-        t1 = smcol[(depth - 1) * 32];
-        if (depth >= 2) { t2 = smcol[(depth - 2) * 32]; Y = fabs(t1 - t2); }
+        t1 = smcol[(depth - 1) * kPostThreads];
+        if (depth >= 2) { t2 = smcol[(depth - 2) * kPostThreads]; Y = fabs(t1 - t2); }
     }
     double dsg = live ? x_cur - t1 : 0.0;                    // sign of the last non-zero difference (0: none yet)
     bool big = false;
-    RfPend pd; pd.np = 0; pd.cnt = 0; pd.has_item = false; pd.item_eff = 0; pd.item_mean = 0;
+    int np = 0, cnt = 0;                                     // this lane's / the warp's cycles waiting for their stress
+    bool has_item = false;
+    double item_eff = 0, item_mean = 0;
+    // (converged code) append the lanes' new cycles to the warp's list; evaluate the list when it may not take another round
+#define RF_APPEND(target_)                                                                     \
+    do {                                                                                       \
+        const unsigned b_ = __ballot_sync(full, has_item);                                     \
+        if (b_) {                                                                              \
+            if (has_item) {                                                                    \
+                const int idx_ = cnt + __popc(b_ & lt_mask);                                   \
+                wb.flat[idx_] = make_double2(item_eff, item_mean);                             \
+                wb.myidx[np * 32 + lane] = (unsigned char)idx_; np++;                          \
+                has_item = false;                                                              \
+            }                                                                                  \
+            cnt += __popc(b_);                                                                 \
+            if (__any_sync(full, np == kRfPend) || cnt > kRfFlat - 32) RF_DRAIN(target_);      \
+        }                                                                                      \
+    } while (0)
+#define RF_DRAIN(target_)                                                                      \
+    do {                                                                                       \
+        if (cnt > 0) {                                                                         \
+            __syncwarp();                                                                      \
+            for (int t_ = lane; t_ < cnt; t_ += 32) {                                          \
+                const double2 it_ = wb.flat[t_];                                               \
+                wb.flat[t_].x = sei_cycle_stress(it_.x, 1.0, it_.y, s_temp);                   \
+            }                                                                                  \
+            __syncwarp();                                                                      \
+            for (int k_ = 0; k_ < np; k_++) (target_) += wb.flat[wb.myidx[k_ * 32 + lane]].x;  \
+            np = 0; cnt = 0;                                                                   \
+            __syncwarp();                                                                      \
+        }                                                                                      \
+    } while (0)
+
+    // ---- committed part: rainflow.reversals + extract_cycles over the pending samples
     int nq = 0;                                              // queued reversals
     for (int r0 = k_done + 1; ; r0 += kRfBatch) {
-        const bool more = r0 <= k_now;                       // (uniform over the warp)
+        const bool more = r0 <= k_now;                       // (uniform over the CTA)
         // extract_cycles(): empty the queues when the next batch might not fit, and after the last row
         if (__any_sync(full, more ? nq > kRfQueue - kRfBatch : nq > 0)) {
+            PT_MARK(2);
             int q = 0;
             while (__any_sync(full, q < nq)) {
                 // One micro-operation per lane, written without branches (the three outcomes would otherwise run one
@@ -634,7 +629,7 @@ __device__ __forceinline__ bool rf_consume(const StepParams& p, int e, int n, bo
                 //   X >= Y, two points    Y contains the starting point: half cycle (t2, t1), popleft, (t2, t1) <- (t1, v), Y <- X
                 //   X >= Y, more points   full cycle (t2, t1): discard its peak and valley, refill (t2, t1) from the copy; v stays
                 const bool act = q < nq;
-                const double v = qcol[min(q, kRfQueue - 1) * 32];
+                const double v = qcol[min(q, kRfQueue - 1) * kPostThreads];
                 const double X = fabs(v - t1);
                 const bool lt = X < Y, two = depth == 2;
                 const bool closing = act && !lt;
@@ -645,21 +640,23 @@ __device__ __forceinline__ bool rf_consume(const StepParams& p, int e, int n, bo
                 else {
                     const double mean = 0.5 * (t2 + t1);
                     acc.x += closing ? mean : 0.0;
-                    pd.has_item = closing && c >= rflm1;
-                    pd.item_eff = two ? 0.5 * Y : Y; pd.item_mean = mean;
+                    has_item = closing && c >= rflm1;
+                    item_eff = two ? 0.5 * Y : Y; item_mean = mean;
                     big = big || (closing && Y > 5);
                     c += closing ? 1 : 0;
-                    if (push) smcol[max(depth - 2, 0) * 32] = t2;
+                    if (push) smcol[max(depth - 2, 0) * kPostThreads] = t2;
                     depth += push ? 1 : (full_c ? -2 : 0);
-                    const double s1 = smcol[max(depth - 1, 0) * 32], s2 = smcol[max(depth - 2, 0) * 32];
+                    const double s1 = smcol[max(depth - 1, 0) * kPostThreads], s2 = smcol[max(depth - 2, 0) * kPostThreads];
                     t2 = consume ? t1 : (full_c ? s2 : t2);
                     t1 = consume ? v : (full_c ? s1 : t1);
                     Y = consume ? X : (full_c ? (depth >= 2 ? fabs(t1 - t2) : inf) : Y);
                     q += consume ? 1 : 0;
                 }
-                rf_pend_append(wb, pd, acc.y, s_temp);
+                PT_COUNT(10, 1);
+                RF_APPEND(acc.y);
             }
             nq = 0;
+            PT_MARK(3);
         }
         if (!more) break;
         // reversals(): eight rows in flight, lock-step over the lanes, no branches.  Rows past k_now repeat the last
@@ -671,87 +668,73 @@ __device__ __forceinline__ bool rf_consume(const StepParams& p, int e, int n, bo
         for (int u = 0; u < kRfBatch; u++) {
             const double d = xb[u] - x_cur;
             const bool flip = live && (dsg * d < 0);
-            if (flip) { qcol[nq * 32] = x_cur; nq++; }
+            if (flip) { qcol[nq * kPostThreads] = x_cur; nq++; }
             dsg = (d != 0) ? d : dsg;
             x_cur = live ? xb[u] : x_cur;
         }
     }
-    rf_pend_drain(wb, pd, acc.y, s_temp);
-    if (big) atomicOr(p.err_flags, 4u);                      // DoD > 5, rainflow_sei_degradation.py:164-167
+    RF_DRAIN(acc.y);
+    PT_MARK(4);
+    // the top two entries go back to the stack copy
+    if (live) { smcol[(depth - 1) * kPostThreads] = t1; if (depth >= 2) smcol[(depth - 2) * kPostThreads] = t2; }
+
+    // ---- evaluation: the provisional end point x_cur on a READ-ONLY view stack[lo .. h) of the committed points
+    double deg = 0;
+    if (evaluate) {                                          // (uniform over the CTA)
+        const int len = k_now + 1;                           // samples in the reference's soc_log
+        int m = c, h = depth, lo = 0, k = 0;
+        double msum = acc.x, fs = 0;
+        int phase = (live && len >= 3) ? 0 : 2;              // 0: closures, 1: residue, 2: done
+        while (__any_sync(full, phase < 2)) {
+            if (phase == 0) {
+                bool closed = false;
+                if (h - lo >= 2) {
+                    const double x2 = smcol[(h - 1) * kPostThreads], x1 = smcol[(h - 2) * kPostThreads];
+                    const double yy = fabs(x2 - x1);
+                    if (!(fabs(x_cur - x2) < yy)) {
+                        closed = true;
+                        const double mean = 0.5 * (x1 + x2);
+                        msum += mean;
+                        if (m >= rflm1) { has_item = true; item_eff = h - lo == 2 ? 0.5 * yy : yy; item_mean = mean; big = big || yy > 5; }
+                        m++;
+                        if (h - lo == 2) lo++; else h -= 2;
+                    }
+                }
+                if (!closed) { phase = 1; k = lo; }
+            } else if (phase == 1) {
+                // "count the remaining ranges as one-half cycles", bottom first; the last of them is list position m-1,
+                // which the slice [rainflow_length-1 : len-1] never includes
+                const double xa = smcol[k * kPostThreads], xb2 = (k + 1 < h) ? smcol[(k + 1) * kPostThreads] : x_cur;
+                const double mean = 0.5 * (xa + xb2);
+                msum += mean;
+                if (k + 1 < h) {
+                    const double rg = fabs(xa - xb2);
+                    if (m >= rflm1) { has_item = true; item_eff = 0.5 * rg; item_mean = mean; big = big || rg > 5; }
+                    k++;
+                } else phase = 2;
+                m++;
+            }
+            RF_APPEND(fs);
+        }
+        RF_DRAIN(fs);
+        if (live) {
+            bool consumed;
+            deg = sei_fade_update(p, i, len, m, rflm1 + 1, msum, acc.y + fs, big, s_temp, consumed);
+            if (consumed) acc.y = 0;         // committed cycles below position m-1 can never be in a later slice
+        }
+    }
+#undef RF_APPEND
+#undef RF_DRAIN
+    PT_MARK(5);
     if (live) {
-        smcol[(depth - 1) * 32] = t1;                        // the top two entries go back to the stack copy
-        if (depth >= 2) smcol[(depth - 2) * 32] = t2;
-        for (int s = 0; s < S; s += 2) *reinterpret_cast<double2*>(stk + s) = make_double2(smcol[s * 32], smcol[(s + 1) * 32]);
+        for (int s = 0; s < S; s += 2)
+            *reinterpret_cast<double2*>(stk + s) = make_double2(smcol[s * kPostThreads], smcol[(s + 1) * kPostThreads]);
         p.rf_dc[i] = (unsigned int)depth | ((unsigned int)c << 16);
         p.rf_acc[i] = acc;
-    } else if (slow) {
-        p.rf_dc[i] = dc | kRfSlowBit;
     }
-    return slow;
-}
-
-// Daily evaluation of one vehicle per lane whose samples are all consumed (WARP-SYNCHRONOUS): the provisional end point
-// x_cur on a READ-ONLY view stack[lo .. h) of the committed points, then calculate_degradation.  Returns the SOH loss.
-__device__ __forceinline__ double rf_evaluate(const StepParams& p, int e, int n, bool active, int k_now, double s_temp,
-                                              const RfWarpBuf wb) {
-    const unsigned full = 0xffffffffu;
-    const int N = p.N;
-    const size_t i = (size_t)e * N + (active ? n : 0);
-    const double* __restrict__ stk = p.rf_stack + i * (size_t)p.rf_S;
-    const int len = k_now + 1;                               // samples in the reference's soc_log
-    int depth = 1, c = 0, rflm1 = 0;
-    double2 acc = make_double2(0.0, 0.0);
-    double x_cur = 0;
-    if (active) {
-        const unsigned int dc = p.rf_dc[i];
-        depth = (int)(dc & 0x7fffu); c = (int)(dc >> 16);
-        acc = p.rf_acc[i];
-        rflm1 = p.rf_len[i] - 1;
-        x_cur = p.hist[(size_t)e * p.RN + (size_t)(k_now & p.Rm) * N + n];
-    }
-    RfPend pd; pd.np = 0; pd.cnt = 0; pd.has_item = false; pd.item_eff = 0; pd.item_mean = 0;
-    bool big = false;
-    int m = c, h = depth, lo = 0, k = 0;
-    double msum = acc.x, fs = 0;
-    int phase = (active && len >= 3) ? 0 : 2;                // 0: closures, 1: residue, 2: done
-    while (__any_sync(full, phase < 2)) {
-        if (phase == 0) {
-            bool closed = false;
-            if (h - lo >= 2) {
-                const double x2 = stk[h - 1], x1 = stk[h - 2];
-                const double yy = fabs(x2 - x1);
-                if (!(fabs(x_cur - x2) < yy)) {
-                    closed = true;
-                    const double mean = 0.5 * (x1 + x2);
-                    msum += mean;
-                    if (m >= rflm1) { pd.has_item = true; pd.item_eff = h - lo == 2 ? 0.5 * yy : yy; pd.item_mean = mean; big = big || yy > 5; }
-                    m++;
-                    if (h - lo == 2) lo++; else h -= 2;
-                }
-            }
-            if (!closed) { phase = 1; k = lo; }
-        } else if (phase == 1) {
-            // "count the remaining ranges as one-half cycles", bottom first; the last of them is list position m-1,
-            // which the slice [rainflow_length-1 : len-1] never includes
-            const double xa = stk[k], xb2 = (k + 1 < h) ? stk[k + 1] : x_cur;
-            const double mean = 0.5 * (xa + xb2);
-            msum += mean;
-            if (k + 1 < h) {
-                const double rg = fabs(xa - xb2);
-                if (m >= rflm1) { pd.has_item = true; pd.item_eff = 0.5 * rg; pd.item_mean = mean; big = big || rg > 5; }
-                k++;
-            } else phase = 2;
-            m++;
-        }
-        rf_pend_append(wb, pd, fs, s_temp);
-    }
-    rf_pend_drain(wb, pd, fs, s_temp);
-    double deg = 0;
-    if (active) {
-        bool consumed;
-        deg = sei_fade_update(p, i, len, m, rflm1 + 1, msum, acc.y + fs, big, s_temp, consumed);
-        if (consumed) p.rf_acc[i] = make_double2(acc.x, 0.0);   // committed cycles below position m-1 can never be in a later slice
-    }
+    PT_MARK(6);
+    if (slow) deg = rf_vehicle_slow(p, e, n, k_done, k_now, evaluate, s_temp);
+    PT_MARK(7);
     return deg;
 }
 
@@ -862,22 +845,16 @@ __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es
 
 // ------------------------------------------------------------------------------------------------ step kernel
 // Work-list entry pushed by the step kernel for envs that need the post kernel (daily degradation and/or reset).
-// Work lists filled by the step kernel.  A record is {env, flags | chunk << 4 | k_done << 12}.
-//   WL_TRIGGER  the env reached the daily evaluation (fleet_environment.py:665-673)
-//   WL_FLUSH    its history ring is about to wrap: the pending samples must be consumed now
-//   WL_RESET    it finished its episode with auto-reset on
-//   WL_SLOW     (added by the rainflow kernel) vehicles of chunk `chunk` still have to consume their samples on the general path
-// TRIGGER | FLUSH entries go to the rainflow kernel's list, TRIGGER | RESET entries to the post kernel's list.
-__device__ __forceinline__ int wl_pack(int wf, int chunk, int k_done) { return wf | (chunk << 4) | (k_done << 12); }
+constexpr int WL_TRIGGER = 1, WL_RESET = 2, WL_FLUSH = 4;
+__device__ __forceinline__ void wl_push(const StepParams& p, int e, int wf) {
+    p.wl[atomicAdd(p.wl_count, 1)] = make_int2(e, wf);
+}
 // Work-list flags of an env whose step k (history sample k+1) has just been taken.  WL_FLUSH: with the next sample the
 // ring would hold more than R rows (samples k_done .. k+2), so the pending ones are consumed now.
-__device__ __forceinline__ void wl_push(const StepParams& p, int e, int env_flags, int k, int k_done) {
+__device__ __forceinline__ int wl_flags(const StepParams& p, int env_flags, int k, int k_done) {
     int wf = ((env_flags & EF_TRIGGER) ? WL_TRIGGER : 0) | ((env_flags & EF_RESET) ? WL_RESET : 0);
     if (p.rf_on && k + 1 - k_done >= p.R - 1) wf |= WL_FLUSH;
-    if (!wf) return;
-    const int2 rec = make_int2(e, wl_pack(wf, 0, k_done));
-    if (p.rf_on && (wf & (WL_TRIGGER | WL_FLUSH))) p.wl_rf[atomicAdd(p.wl_count + 2, 1)] = rec;
-    if (wf & (WL_TRIGGER | WL_RESET)) p.wl[atomicAdd(p.wl_count, 1)] = rec;
+    return wf;
 }
 
 // Shared-memory layout (dynamic): EnvS envs[B] | double contrib[kNQ][slots] | double sums[kNQ][B] |
@@ -1081,7 +1058,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
             }
             p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
             st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, es.k_done), keep);
-            wl_push(p, e, es.flags, es.t - es.t_start, es.k_done);   // degradation first, reset afterwards, like the reference
+            const int wf = wl_flags(p, es.flags, es.t - es.t_start, es.k_done);
+            if (wf) wl_push(p, e, wf);   // the post kernel evaluates the degradation first and resets afterwards, like the reference
         }
         p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
         p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
@@ -1402,7 +1380,8 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
                 }
                 p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = ep_ret;
                 st_keep_v4(p.env4 + e, make_int4(es.t + 1, es.t_start, es.ep_count, es.k_done), keep);
-                wl_push(p, e, es.flags, es.t - es.t_start, es.k_done);
+                const int wf = wl_flags(p, es.flags, es.t - es.t_start, es.k_done);
+                if (wf) wl_push(p, e, wf);
                 p.env_f64[(size_t)EF_REWARD64 * p.E + e] = reward;
                 p.env_f64[(size_t)EF_CASHFLOW * p.E + e] = cashflow;
                 p.env_f64[(size_t)EF_OVERLOAD * p.E + e] = overload;
@@ -1585,65 +1564,14 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
     PF_FLUSH(8);
 }
 
-// --------------------------------------------------------------------------------- rainflow kernel + post kernel
-// After the step kernel, on the same stream:
-//   fleet_rf_kernel    consumes the pending history samples of every env on the rainflow list (daily evaluation due, or
-//                      history ring about to wrap): one WARP per (env, 32 vehicles), persistent grid, items fetched
-//                      dynamically.  Small and register-lean on purpose: it is latency bound (serial three-point stacks),
-//                      so what matters is how many warps are resident.
-//   fleet_post_kernel  one CTA per env on the post list: finishes vehicles the rainflow kernel left to the general path,
-//                      runs the daily evaluation (fleet_environment.py:665-673: RainflowSeiDegradation /
-//                      EmpiricalDegradation.calculate_degradation, soh -= degradation) and then, if the episode ended
-//                      with auto-reset on, FleetEnv.reset (:330-434) — the order in which a SubprocVecEnv worker runs them.
-constexpr int kRfWarps = 4;        // independent warps per CTA of the rainflow kernel
-
-__host__ __device__ inline size_t rf_warp_smem(int S) {       // stack copy + reversal queue + stress list of one warp
-    return (size_t)(S + kRfQueue) * 32 * 8 + (size_t)kRfFlat * 16 + (size_t)kRfPend * 32;
-}
-
-__global__ void __launch_bounds__(kRfWarps * 32) fleet_rf_kernel(const __grid_constant__ StepParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem_raw + (size_t)warp * rf_warp_smem(p.rf_S);
-    double* sm_stack = reinterpret_cast<double*>(wbase);                       // [rf_S][32]
-    double* sm_queue = sm_stack + (size_t)p.rf_S * 32;                         // [kRfQueue][32]
-    RfWarpBuf wb;
-    wb.flat = reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * 32);    // [kRfFlat]
-    wb.myidx = reinterpret_cast<unsigned char*>(wb.flat + kRfFlat);            // [kRfPend][32]
-    const int nch = p.rf_nch;
-    const int items = p.wl_count[2] * nch;                   // one item per (entry, 32-vehicle chunk)
-    const int nw = (int)gridDim.x * kRfWarps;
-    const double temp_ref = 25, k_temp = 6.93E-2;
-    const double s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
-
-    // first item static, further ones from a counter; the next item's list record and env4 are fetched while the
-    // current one is processed
-    int w = (int)blockIdx.x * kRfWarps + warp;
-    int2 ent = make_int2(0, 0);
-    int4 ev = make_int4(0, 0, 0, 0);
-    if (w < items) { ent = p.wl_rf[w / nch]; ev = p.env4[ent.x]; }
-    while (w < items) {
-        int w_next = 0;
-        if (lane == 0) w_next = atomicAdd(p.wl_count + 3, 1) + nw;
-        w_next = __shfl_sync(0xffffffffu, w_next, 0);
-        int2 ent_next = make_int2(0, 0);
-        int4 ev_next = make_int4(0, 0, 0, 0);
-        if (w_next < items) { ent_next = p.wl_rf[w_next / nch]; ev_next = p.env4[ent_next.x]; }
-        const int chunk = w - (w / nch) * nch;
-        const int e = ent.x, wf = ent.y & 15, k_done = (int)((unsigned)ent.y >> 12);
-        const int k_now = ev.x - ev.y;                       // newest history sample (samples 0..k_now exist)
-        const int n = chunk * 32 + lane;
-        const bool slowed = rf_consume(p, e, n, n < p.N, k_done, k_now, s_temp, sm_stack + lane, sm_queue + lane, wb);
-        const bool any_slow = __any_sync(0xffffffffu, slowed);
-        if (lane == 0) {
-            if (chunk == 0) reinterpret_cast<int*>(p.env4 + e)[3] = k_now;     // k_done: samples up to k_now are consumed
-            // vehicles left to the general path: the post kernel finishes them (a TRIGGER / RESET entry is on its list anyway)
-            if (any_slow && !(wf & (WL_TRIGGER | WL_RESET))) p.wl[atomicAdd(p.wl_count, 1)] = make_int2(e, wl_pack(WL_SLOW, chunk, k_done));
-        }
-        w = w_next; ent = ent_next; ev = ev_next;
-    }
-}
-
+// ------------------------------------------------------------------------------------------------ post kernel
+// One CTA of kPostThreads threads per work-list entry (persistent grid, entries fetched dynamically), one vehicle per
+// thread.  An entry is an env that, in this step,
+//   WL_TRIGGER  reached the daily evaluation (fleet_environment.py:665-673): consume the pending history samples, then
+//               RainflowSeiDegradation / EmpiricalDegradation.calculate_degradation, soh -= degradation;
+//   WL_FLUSH    is about to wrap its history ring: consume the pending samples (no evaluation);
+//   WL_RESET    finished its episode with auto-reset on: FleetEnv.reset (:330-434) AFTER the evaluation, i.e. the order in
+//               which a SubprocVecEnv worker runs them.
 // Auto-reset of one finished env by `nthr` cooperating threads (rank `tid`): FleetEnv.reset as the SubprocVecEnv
 // worker calls it right after a done step.  `ev` is the env's {t, t_start, ep_count} before the reset.
 template <bool kNorm, bool kAux>
@@ -1656,22 +1584,24 @@ __device__ __forceinline__ void post_reset_env(const StepParams& p, int e, int4 
         p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = 0;
     }
 }
-// The last CTA of the post kernel to finish clears both work lists for the next step.
+// The last CTA of a post kernel to finish clears the work list for the next step.
 __device__ __forceinline__ void post_finish_lists(const StepParams& p) {
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int d = atomicAdd(p.wl_done, 1u);
-        if (d == gridDim.x - 1) { p.wl_count[0] = 0; p.wl_count[1] = 0; p.wl_count[2] = 0; p.wl_count[3] = 0; *p.wl_done = 0; }
+        if (d == gridDim.x - 1) { p.wl_count[0] = 0; p.wl_count[1] = 0; *p.wl_done = 0; }
     }
 }
 
 template <bool kNorm, bool kAux>
 __global__ void __launch_bounds__(kPostThreads, 10) fleet_post_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sm_stack = reinterpret_cast<double*>(smem_raw);                    // [rf_S][kPostThreads]
+    double* sm_queue = sm_stack + (size_t)p.rf_S * kPostThreads;               // [kRfQueue][kPostThreads]
     RfWarpBuf wb;                                                              // per warp
-    wb.flat = reinterpret_cast<double2*>(smem_raw) + (threadIdx.x >> 5) * kRfFlat;
-    wb.myidx = reinterpret_cast<unsigned char*>(reinterpret_cast<double2*>(smem_raw) + (kPostThreads / 32) * kRfFlat) +
-               (threadIdx.x >> 5) * (kRfPend * 32);
+    wb.flat = reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * kPostThreads) + (threadIdx.x >> 5) * kRfFlat;
+    wb.myidx = reinterpret_cast<unsigned char*>(reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * kPostThreads) +
+                                                (kPostThreads / 32) * kRfFlat) + (threadIdx.x >> 5) * (kRfPend * 32);
     __shared__ int s_w;
     __shared__ int2 s_ent;
     __shared__ int4 s_ev;
@@ -1692,7 +1622,7 @@ __global__ void __launch_bounds__(kPostThreads, 10) fleet_post_kernel(const __gr
         const int w = s_w;
         if (w >= count) break;
         const int2 ent = s_ent;
-        const int e = ent.x, wf = ent.y & 15, chunk = (ent.y >> 4) & 255, k_done = (int)((unsigned)ent.y >> 12);
+        const int e = ent.x, wf = ent.y;
         const int4 ev = s_ev;                           // {t (already advanced), t_start, ep_count, k_done}
         const int k_now = ev.x - ev.y;                  // newest history sample (samples 0..k_now exist)
         int w_next = 0;
@@ -1702,20 +1632,14 @@ __global__ void __launch_bounds__(kPostThreads, 10) fleet_post_kernel(const __gr
             w_next = atomicAdd(p.wl_count + 1, 1) + (int)gridDim.x;
             if (w_next < count) { ent_next = p.wl[w_next]; ev_next = p.env4[ent_next.x]; }
         }
-        if (p.rf_on && (wf & (WL_TRIGGER | WL_SLOW))) {
-            const bool evaluate = (wf & WL_TRIGGER) != 0;
-            const int n_lo = evaluate ? 0 : chunk * 32, n_hi = evaluate ? N : min(N, chunk * 32 + 32);
-            for (int n0 = n_lo; n0 < n_hi; n0 += kPostThreads) {   // (all lanes of a warp go in together)
+        PT_START();
+        PT_COUNT(11, 1);
+        if (p.rf_on && (wf & (WL_TRIGGER | WL_FLUSH))) {
+            PT_COUNT(12, 1);
+            for (int n0 = 0; n0 < N; n0 += kPostThreads) {   // (all lanes of a warp go in together)
                 const int n = n0 + tid;
-                const bool active = n < n_hi;
-                // vehicles the rainflow kernel left to the general path: consume (and evaluate) there
-                const bool slow = active && (p.rf_dc[(size_t)e * N + n] & kRfSlowBit) != 0;
-                double deg = 0;
-                if (slow) deg = rf_vehicle_slow(p, e, n, k_done, k_now, evaluate, s_temp);
-                if (evaluate) {
-                    const double d2 = rf_evaluate(p, e, n, active && !slow, k_now, s_temp, wb);
-                    if (!slow) deg = d2;
-                }
+                const double deg = rf_vehicle(p, e, n, n < N, ev.w, k_now, (wf & WL_TRIGGER) != 0, s_temp, sm_stack + tid,
+                                              sm_queue + tid, wb);
                 if (deg != 0) atomicAdd(&s_deg, deg);
             }
         } else if (wf & WL_TRIGGER) {                   // EmpiricalDegradation: the last two samples only
@@ -1731,10 +1655,13 @@ __global__ void __launch_bounds__(kPostThreads, 10) fleet_post_kernel(const __gr
             }
         }
         __syncthreads();
+        PT_MARK(8);
         if (tid == 0 && s_deg != 0)
             atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
         if (wf & WL_RESET) post_reset_env<kNorm, kAux>(p, e, ev, tid, kPostThreads);
+        else if (tid == 0 && p.rf_on) p.env4[e] = make_int4(ev.x, ev.y, ev.z, k_now);   // samples up to k_now are consumed
         __syncthreads();                                 // everybody has read s_w / s_ent / s_ev / s_deg
+        PT_MARK(9);
         if (tid == 0) { s_w = w_next; s_ent = ent_next; s_ev = ev_next; s_deg = 0; }
     }
     post_finish_lists(p);
@@ -1886,9 +1813,9 @@ struct FleetHandle {
     int64_t bytes = 0;
     int64_t launches = 0;
     std::string err;
-    size_t smem_step = 0, smem_post = 0, smem_pf = 0, smem_rf = 0;
+    size_t smem_step = 0, smem_post = 0, smem_pf = 0;
     int grid_pf = 0, use_pf = 0;
-    int grid = 0, grid_post = 0, grid_rf = 0, need_post = 0, num_sms = 0;
+    int grid = 0, grid_post = 0, need_post = 0, num_sms = 0;
     int max_smem_optin = 0;
     double* charge_log_buf = nullptr;   // fleet_enable_charge_log
     int host_zerocopy = 1;              // fleet_step_host: use page-locked host buffers in place (FLEETSTEP_HOST_ZEROCOPY)
@@ -2261,9 +2188,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     if ((rc = dev_alloc(h, &p.last_deg, EN))) return rc;
     if ((rc = dev_alloc(h, &p.stats, (size_t)kStatStripes * FLEET_S__COUNT))) return rc;
     if ((rc = dev_alloc(h, &p.err_flags, (size_t)4))) return rc;
-    const int rf_nch = (N + 31) / 32;
-    if ((rc = dev_alloc(h, &p.wl, (size_t)E * (size_t)(rf_on ? 1 + rf_nch : 1)))) return rc;
-    if ((rc = dev_alloc(h, &p.wl_rf, (size_t)(rf_on ? E : 1)))) return rc;
+    if ((rc = dev_alloc(h, &p.wl, (size_t)E))) return rc;
     if (rf_on) {
         if ((rc = dev_alloc(h, &p.rf_stack, EN * (size_t)rfS))) return rc;
         if ((rc = dev_alloc(h, &p.rf_dc, EN))) return rc;
@@ -2276,7 +2201,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     if ((rc = dev_alloc(h, &p.wl_count, (size_t)4))) return rc;
     if ((rc = dev_alloc(h, &p.wl_done, (size_t)4))) return rc;
 
-    p.rf_on = rf_on ? 1 : 0; p.rf_S = rfS; p.rf_X = rfX; p.rf_P = rfP; p.rf_nch = rf_nch;
+    p.rf_on = rf_on ? 1 : 0; p.rf_S = rfS; p.rf_X = rfX; p.rf_P = rfP;
     p.E = E; p.N = N; p.T = T; p.R = R; p.Rm = R - 1; p.L = c.episode_steps; p.D = h->D; p.Ha = Ha; p.Hb = Hb; p.hdr_stride = hdr_stride;
     p.B = N >= kThreads ? 1 : kThreads / N;
     p.RN = (unsigned long long)R * (unsigned long long)N;
@@ -2319,29 +2244,19 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
                  h->D, h->max_smem_optin);
         return fail(h, FLEET_E_INVALID, buf);
     }
-    // rainflow kernel (one warp per (env, 32 vehicles)) and post kernel (one CTA per env)
+    // post kernel: one CTA of kPostThreads threads per work-list env; shared memory = the vehicles' stack copies + the
+    // per-batch reversal lists
     h->num_sms = prop.multiProcessorCount;
     h->need_post = (c.calc_degradation || c.auto_reset) ? 1 : 0;
-    h->smem_post = align16((size_t)(kPostThreads / 32) * (kRfFlat * 16 + kRfPend * 32));
+    h->smem_post = align16((size_t)(rfS + kRfQueue) * kPostThreads * 8 + (size_t)(kPostThreads / 32) * (kRfFlat * 16 + kRfPend * 32));
+    if ((int64_t)h->smem_post > (int64_t)h->max_smem_optin) return fail(h, FLEET_E_INVALID, "rf_stack_depth does not fit the post kernel's shared memory");
     {
         int per_sm = 1;
         CUDA_TRY(h, cudaFuncSetAttribute(pick_post(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post));
         CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post(h), kPostThreads, h->smem_post));
         if (per_sm < 1) per_sm = 1;
         const int64_t g = (int64_t)h->num_sms * per_sm;
-        const int64_t cap = (int64_t)E * (rf_on ? 1 + rf_nch : 1);
-        h->grid_post = (int)(g < cap ? g : cap);
-    }
-    if (rf_on) {
-        h->smem_rf = align16((size_t)kRfWarps * rf_warp_smem(rfS));
-        if ((int64_t)h->smem_rf > (int64_t)h->max_smem_optin) return fail(h, FLEET_E_INVALID, "rf_stack_depth does not fit the rainflow kernel's shared memory");
-        int per_sm = 1;
-        CUDA_TRY(h, cudaFuncSetAttribute(fleet_rf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_rf));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fleet_rf_kernel, kRfWarps * 32, h->smem_rf));
-        if (per_sm < 1) per_sm = 1;
-        const int64_t g = (int64_t)h->num_sms * per_sm;
-        const int64_t cap = ((int64_t)E * rf_nch + kRfWarps - 1) / kRfWarps;
-        h->grid_rf = (int)(g < cap ? g : cap);
+        h->grid_post = (int)(g < E ? g : E);
     }
     h->smem_step = sm;
     {
@@ -2421,8 +2336,7 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     else pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
     h->launches++;
     if (tev) cudaEventRecord(tev[1], (cudaStream_t)stream);
-    if (h->need_post) {   // rainflow consumption, daily degradation, then auto-reset, for the envs the step kernel put on the work lists
-        if (p.rf_on) { fleet_rf_kernel<<<h->grid_rf, kRfWarps * 32, h->smem_rf, (cudaStream_t)stream>>>(p); h->launches++; }
+    if (h->need_post) {   // daily degradation, then auto-reset, for the envs the step kernel put on the work list
         pick_post(h)<<<h->grid_post, kPostThreads, h->smem_post, (cudaStream_t)stream>>>(p);
         h->launches++;
     }
