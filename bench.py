@@ -69,6 +69,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-envs", type=int, default=2048)
+    ap.add_argument("--raw-inputs", action="store_true",
+                    help="skip the CSV text round trip of the synthetic inputs (saves ~8 s of start-up; diagnostic runs)")
     ap.add_argument("--settle-episodes", type=int, default=0,
                     help="extra untimed episodes after de-phasing (rainflow_length converges to its running maximum)")
     args = ap.parse_args()
@@ -95,7 +97,12 @@ def build_workload(args):
     if args.cfg["minutes"] == 60:
         over.update(freq="1h", minutes=60, time_steps_per_hour=1)
     cfg = default_config(args.use_case, episode_length=args.episode_hours, seed=0, **over)
-    built = build_fleet(cfg, FleetInputs(sched, price, tariff, load, pv), auto_reset=True,
+    inputs = FleetInputs(sched, price, tariff, load, pv)
+    if not getattr(args, "raw_inputs", False):
+        # the fleet exactly as the unmodified reference would read it from schedule.write_reference_csvs' files
+        # (pandas' CSV float parser moves ~1/8 of the values by one ulp; tests/test_host_logic.py)
+        inputs = inputs.csv_round_trip()
+    built = build_fleet(cfg, inputs, auto_reset=True,
                         carry_degradation_state=bool(args.carry), seed=0, time_picker="random")
     return built
 

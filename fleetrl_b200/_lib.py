@@ -22,6 +22,7 @@ EXPORTS = [
     "fleet_reset", "fleet_step", "fleet_step_host", "fleet_set_next_start", "fleet_get_state", "fleet_set_state",
     "fleet_field_info", "fleet_get_stats", "fleet_reset_stats", "fleet_check_errors", "fleet_launch_count",
     "fleet_device_bytes", "fleet_last_error", "fleet_set_timing", "fleet_get_timing", "fleet_step_kernel_name", "fleet_policy_actions", "fleet_policy_reset", "fleet_enable_charge_log",
+    "fleet_enable_log", "fleet_log_layout", "fleet_read_log", "fleet_state_bytes", "fleet_export_state", "fleet_import_state",
 ]
 
 
@@ -62,6 +63,13 @@ def load_library(path: str = LIB_PATH):
     L.fleet_policy_actions.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.fleet_policy_reset.argtypes = [vp, vp]
     L.fleet_enable_charge_log.argtypes = [vp, i32]
+    L.fleet_enable_log.argtypes = [vp, vp, i32, i32]
+    L.fleet_log_layout.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.fleet_read_log.argtypes = [vp, vp, vp, vp]
+    L.fleet_state_bytes.argtypes = [vp]
+    L.fleet_state_bytes.restype = i64
+    L.fleet_export_state.argtypes = [vp, vp, vp]
+    L.fleet_import_state.argtypes = [vp, vp, vp]
     L.fleet_step_kernel_name.argtypes = [vp]
     L.fleet_step_kernel_name.restype = C.c_char_p
     L.fleet_set_timing.argtypes = [vp, i32]
@@ -219,6 +227,47 @@ class FleetStepHandle:
     def enable_charge_log(self, enable=True):
         """Keep EvCharger's per-vehicle charge_log of every step (field "charge_log"); off by default."""
         self._check(self.lib.fleet_enable_charge_log(self._h, 1 if enable else 0), "fleet_enable_charge_log")
+
+    # -- device-side DataLogger (data_logger.py:21-68) for selected envs
+    def enable_log(self, env_ids, rows_per_env):
+        ids = np.ascontiguousarray(env_ids, dtype=np.int32)
+        self._check(self.lib.fleet_enable_log(self._h, ids.ctypes.data, len(ids), int(rows_per_env)), "fleet_enable_log")
+        self._log_ids = ids
+
+    def read_log(self):
+        """-> list (one entry per logged env) of dicts of arrays, oldest row first: ep_count, time_idx, reward, cashflow,
+        penalties, overload, soc_viol, kind (1 reset row / 2 step with daily degradation / 0 other step), action [rows, N],
+        degradation [rows, N], charging_energy [rows, N], soh [rows, N], obs [rows, D]."""
+        n, cap, rd = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.fleet_log_layout(self._h, C.byref(n), C.byref(cap), C.byref(rd)), "fleet_log_layout")
+        n, cap, rd = n.value, cap.value, rd.value
+        rows = np.zeros((max(n, 1), max(cap, 1), max(rd, 1)))
+        counts = np.zeros(max(n, 1), np.int64)
+        self._check(self.lib.fleet_read_log(self._h, rows.ctypes.data, counts.ctypes.data, _stream_ptr(self.device)), "fleet_read_log")
+        N, out = self.N, []
+        for l in range(n):
+            cnt = int(counts[l])
+            r = rows[l, :cnt] if cnt <= cap else np.roll(rows[l], -(cnt % cap), axis=0)
+            out.append({"env": int(self._log_ids[l]), "rows_total": cnt, "ep_count": r[:, 0].astype(np.int64),
+                        "time_idx": r[:, 1].astype(np.int64), "reward": r[:, 2], "cashflow": r[:, 3], "penalties": r[:, 4],
+                        "overload": r[:, 5], "soc_viol": r[:, 6], "kind": r[:, 7].astype(np.int64),
+                        "action": r[:, 8:8 + N], "degradation": r[:, 8 + N:8 + 2 * N],
+                        "charging_energy": r[:, 8 + 2 * N:8 + 3 * N], "soh": r[:, 8 + 3 * N:8 + 4 * N],
+                        "obs": r[:, 8 + 4 * N:].astype(np.float32)})
+        return out
+
+    # -- checkpoint / resume
+    def export_state(self):
+        """The complete env state of the handle as one opaque uint8 array (fleet_export_state)."""
+        buf = np.empty(int(self.lib.fleet_state_bytes(self._h)), np.uint8)
+        self._check(self.lib.fleet_export_state(self._h, buf.ctypes.data, _stream_ptr(self.device)), "fleet_export_state")
+        return buf
+
+    def import_state(self, blob):
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        if b.size != int(self.lib.fleet_state_bytes(self._h)):
+            raise FleetStepError("import_state: blob size does not match this handle")
+        self._check(self.lib.fleet_import_state(self._h, b.ctypes.data, _stream_ptr(self.device)), "fleet_import_state")
 
     def set_timing(self, enable=True):
         self._check(self.lib.fleet_set_timing(self._h, 1 if enable else 0), "fleet_set_timing")

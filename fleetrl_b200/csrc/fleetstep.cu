@@ -130,7 +130,8 @@ struct StepParams {
     int* wl_count;            // [4] {entries, next entry to fetch, -, -}
     unsigned int* wl_done;    // [1]
     // persistent step kernel geometry (host-computed so that the kernel reads it from the constant bank, not registers)
-    int pf_B, pf_bulk, pf_ntiles, pf_cslots, pf_cper, pf_pair;      // pf_B: envs per tile = kPfCompute / N
+    int pf_B, pf_bulk, pf_ntiles, pf_cslots, pf_cper, pf_pair;      // pf_B: envs per tile = kPfSlots / N
+    int pf_obs2;                                              // D and Ha are even: a vehicle pair's observation terms are 8-byte aligned
     unsigned int pf_tile_hist;                                // B * RN: history elements per tile (< 2^32, checked at create)
     int pf_envs_b, pf_contrib_b, pf_obs_b;                    // bytes of one env-scratch / contribution / obs buffer
     int pf_off_contrib, pf_off_sums, pf_off_obs, pf_off_stage;   // shared-memory offsets
@@ -340,8 +341,17 @@ __device__ unsigned long long g_post_clk[16];
 constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one work-list env per CTA, one vehicle per thread)
 constexpr int kRfBatch = 8;        // history rows in flight per lane while scanning
 constexpr int kRfQueue = 12;       // reversal values queued per lane between two runs of the three-point stack
-constexpr int kRfPend = 4;         // cycles per lane ...
-constexpr int kRfFlat = 64;        // ... and per warp waiting for their stress evaluation (evaluated by the whole warp)
+#ifndef RF_PEND
+#define RF_PEND 4
+#endif
+#ifndef RF_FLAT
+#define RF_FLAT 64
+#endif
+#ifndef POST_MIN_CTAS
+#define POST_MIN_CTAS 10
+#endif
+constexpr int kRfPend = RF_PEND;   // cycles per lane ...
+constexpr int kRfFlat = RF_FLAT;   // ... and per warp waiting for their stress evaluation (evaluated by the whole warp)
 
 // SEI stress of one cycle: rainflow_sei_degradation.py:68-79 with effective DoD = clip(range*count, 0, 1) (:170)
 __device__ __forceinline__ double sei_cycle_stress(double range, double count, double mean, double s_temp) {
@@ -780,6 +790,7 @@ __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es
     const double cap = soh * p.cap0;                                // episode.battery_cap[car]
     double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
     double num = 0;                                                 // next_soc = soc + num / cap
+#ifdef EV_BRANCHY
     if (a >= 0) {                                                   // ev_charger.py:98-156
         const double dem = (tgt - soc) * cap;
         const double req = p.P * a * p.dt;
@@ -815,6 +826,36 @@ __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es
         q_en = 0;
         atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
     }
+#else
+    // The charging (ev_charger.py:98-156) and the discharging (:159-206) branch are both evaluated and the action's sign
+    // selects: in a warp of vehicles with mixed actions both would run anyway, one after the other with half the lanes
+    // masked; written this way their two dependency chains interleave.  Every selected value is produced by exactly the
+    // operations of its branch, so the results are bit-identical to the branching form (-DEV_BRANCHY).
+    {
+        const bool chg = a >= 0, dis = a < 0, th1 = there == 1;
+        const double req = p.P * a * p.dt;
+        const double dem = (tgt - soc) * cap;                       // charging side
+        const double dq = req - dem;
+        const double pen_q = p.pen_oc * (dq * dq);
+        const double pen_c = (req * p.eta_c > dem) ? (pen_q > p.clip_oc ? pen_q : p.clip_oc) : 0.0;
+        const double en_c = th1 ? fmin(dem / p.eta_c, req) : 0.0;   // IEEE divide: SOC must be bit-exact
+        double ge = en_c - es.pv_share;
+        ge = ge > 0 ? ge : 0;
+        const double left = -1 * soc * cap;                         // discharging side
+        const double dl = left - req;
+        const double pen_d = (req * p.eta_d < left && there != 0) ? p.pen_oc * (dl * dl) : 0.0;
+        const double en_d = th1 ? fmax(left, req) : 0.0;
+        c_oc = chg ? pen_c : (dis ? pen_d : 0.0);
+        c_inv = ((chg || dis) && !th1 && fabs(a) > 0.05) ? p.pen_inv * (a * a) : 0.0;
+        num = chg ? en_c * p.eta_c : (dis ? en_d : 0.0);
+        q_en = chg ? en_c : (dis ? en_d : 0.0);                     // charge_log, ev_charger.py:212
+        c_cost = chg ? ge * es.S * p.mult : 0.0;
+        c_cr = chg ? es.F_cr * ge : 0.0;
+        c_rev = dis ? -1 * en_d * es.Rfac : 0.0;
+        c_dr = dis ? es.F_dr * en_d : 0.0;
+        if (!(chg || dis)) atomicOr(p.err_flags, 1u);               // NaN action: TypeError ev_charger.py:209
+    }
+#endif
     q_ath = a * (double)there;                                      // fleet_environment.py:491
     // ev_charger.py:128,189 ; :470.  num == 0 (absent vehicle, zero action) adds exactly 0: skipping the division there
     // is bit-identical and keeps the warp out of the slow path of the f64 divide.
@@ -1088,8 +1129,25 @@ __global__ void __launch_bounds__(kThreads, kMinCtasPerSm) fleet_step_kernel(con
 #ifndef KPFCOMPUTE
 #define KPFCOMPUTE 256
 #endif
-constexpr int kPfCompute = KPFCOMPUTE;           // compute threads (one per slot of a tile)
-constexpr int kPfThreads = kPfCompute + 64;     // + two epilogue warps
+// slots ((env, EV) pairs) of a tile: B = pf_slots / N envs
+// kV = vehicles per compute thread.  kV = 1: one thread per slot, 8 compute warps, 2 CTAs/SM.  kV = 2 (even N): a thread owns
+// two neighbouring vehicles of one env; every array access is twice as wide (16-byte state copies, float2 observation
+// stores), the per-thread overhead (addresses, hand-offs, loop control) is paid once per pair and the pair's contributions
+// are added in registers: 4 compute warps per CTA, 3 CTAs/SM.
+#ifndef PF2_SLOTS
+#define PF2_SLOTS 384
+#endif
+#ifndef PF_DEFAULT_V
+#define PF_DEFAULT_V 1
+#endif
+__host__ __device__ constexpr int pf_slots(int kV) { return kV == 2 ? PF2_SLOTS : KPFCOMPUTE; }
+__host__ __device__ constexpr int pf_compute_threads(int kV) { return pf_slots(kV) / kV; }
+__host__ __device__ constexpr int pf_threads(int kV) { return pf_compute_threads(kV) + 64; }     // + two epilogue warps
+// register cap per thread: kV = 2 wants ~140 uncapped; 112 keeps three CTAs (12 compute warps) per SM with 48 bytes of spills
+#ifndef PF2_MAXREG
+#define PF2_MAXREG 128
+#endif
+__host__ __device__ constexpr int pf_maxreg(int kV) { return kV == 2 ? PF2_MAXREG : 96; }
 
 struct PfEnv {   // per-env scratch of a tile (shared memory, triple buffered)
     int t, t_start, ep_count, flags;
@@ -1101,24 +1159,25 @@ struct PfEnv {   // per-env scratch of a tile (shared memory, triple buffered)
 #define KPFSTAGES 2
 #endif
 // input stage of the pf kernel: the per-slot inputs of one tile, structure of arrays indexed by the slot's thread
-constexpr int kPfStA32 = 0, kPfStHl = 4 * KPFCOMPUTE, kPfStHv = 8 * KPFCOMPUTE, kPfStSoc = 12 * KPFCOMPUTE,
-              kPfStSoh = 20 * KPFCOMPUTE, kPfStSdeg = 28 * KPFCOMPUTE, kPfStR0 = 36 * KPFCOMPUTE, kPfStR1 = 52 * KPFCOMPUTE,
-              kPfStageBytes = 68 * KPFCOMPUTE, kPfStages = KPFSTAGES;
+// (byte offsets for a tile capacity of KS slots)
+#define PF_STAGE_LAYOUT(KS)                                                                                              \
+    constexpr int kPfStA32 = 0, kPfStHl = 4 * (KS), kPfStHv = 8 * (KS), kPfStSoc = 12 * (KS), kPfStSoh = 20 * (KS),        \
+                  kPfStSdeg = 28 * (KS), kPfStR0 = 36 * (KS), kPfStR1 = 52 * (KS), kPfStageBytes = 68 * (KS);             \
+    (void)kPfStA32; (void)kPfStHl; (void)kPfStHv; (void)kPfStSoc; (void)kPfStSoh; (void)kPfStSdeg; (void)kPfStR0; (void)kPfStR1
+constexpr int kPfStages = KPFSTAGES;
+__host__ __device__ constexpr int pf_stage_bytes(int kV) { return 68 * pf_slots(kV); }
 // measured on B200 at cfg2: 2 CTAs/SM x 10 warps with ~100 registers (no spills, L1 left for the tables) beat 3 CTAs/SM
 // at 64 registers by 5-6 %
 #ifndef KPFOUT
 #define KPFOUT 3
 #endif
-#ifndef KPFCTAS
-#define KPFCTAS 2
-#endif
 constexpr int kPfOut = KPFOUT;     // output buffers (contributions + obs tile): the epilogue may lag two tiles behind
 constexpr int kPfEnvs = 4;    // env-scratch buffers: staged three tiles ahead
 // Even N: neighbouring vehicles' contributions are added in the compute warp (one shuffle), halving the buffer.
 __host__ __device__ inline int pf_contrib_slots(int B, int N) { return (N & 1) ? B * N : (B * N) / 2; }
-__host__ __device__ inline size_t pf_smem_bytes(int B, int N, int D) {
+__host__ __device__ inline size_t pf_smem_bytes(int B, int N, int D, int kV) {
     return align16(kPfEnvs * align16((size_t)B * sizeof(PfEnv)) + kPfOut * align16((size_t)kNQ * pf_contrib_slots(B, N) * 8) +
-                   2 * align16((size_t)kNQ * B * 8) + kPfOut * align16((size_t)B * D * 4)) + (size_t)kPfStages * kPfStageBytes;
+                   2 * align16((size_t)kNQ * B * 8) + kPfOut * align16((size_t)B * D * 4)) + (size_t)kPfStages * pf_stage_bytes(kV);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
@@ -1171,8 +1230,10 @@ __device__ unsigned long long g_pf_clk[16];
 #endif
 // kLog: keep EvCharger's charge_log (fleet_enable_charge_log); a template flag so that the default instance carries
 // neither the extra live register nor the store.
-template <bool kNorm, bool kAux, bool kLog>
-__global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(const StepParams p) {
+template <bool kNorm, bool kAux, bool kLog, int kV>
+__global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fleet_step_pf_kernel(const StepParams p) {
+    constexpr int kPfCompute = pf_compute_threads(kV);
+    PF_STAGE_LAYOUT(pf_slots(kV));
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = p.N, B = p.pf_B, D = p.D;
     const int cstride = B * N;
@@ -1396,11 +1457,15 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
     }
 
     // ======================================================================= compute warps
-    const int j = tid;
+    // thread tid owns the kV neighbouring slots j .. j+kV-1 of every tile (kV == 2: N is even, so both are vehicles n, n+1 of
+    // the same env b and j, n are even)
+    const int j = tid * kV;
     const int b = (N == 1) ? j : (int)__umulhi((unsigned)j, p.n_magic);     // slot -> (env of tile, EV): same for every tile
     const int n = j - b * N;
     const bool slot = j < cstride;
-    const int hpos = n < p.Ha ? 2 * N + n : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (n - p.Ha);
+    auto hdr_pos = [&](int q) { return q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha); };
+    const int hpos = hdr_pos(n), hpos1 = hdr_pos(n + 1);
+    const bool wide_obs = kV == 2 && p.pf_obs2;               // float2 observation stores are aligned (D and Ha even)
 
     // Input pipeline: the per-slot inputs of a tile (action, soc, hours_left, soh, previous history row, both halves of
     // ev_rec[t+1], the header element) are copied by the slot's OWN thread into a shared-memory stage with cp.async
@@ -1426,23 +1491,43 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
             const int k = ev.x - ev.y;
             const int t1 = min(ev.x + 1, p.T - 1);
             const int4* rp = reinterpret_cast<const int4*>(p.ev_rec + (size_t)t1 * N + n);
-            cp_async4_hint(st + kPfStA32 + j * 4, p.actions + i, stream);
+            const double* hp = p.hist + ((size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)((k & p.Rm) * N));
+            const float* hd = p.hdr + (size_t)t1 * p.hdr_stride + n;
+            if (kV == 1) {
+                cp_async4_hint(st + kPfStA32 + j * 4, p.actions + i, stream);
 #ifndef PF_NOSTATE
-            cp_async8_hint(st + kPfStSoc + j * 8, p.soc + i, stream);
-            cp_async4_hint(st + kPfStHl + j * 4, p.hl + i, stream);
-            cp_async8_hint(st + kPfStSoh + j * 8, p.soh + i, stream);
+                cp_async8_hint(st + kPfStSoc + j * 8, p.soc + i, stream);
+                cp_async4_hint(st + kPfStHl + j * 4, p.hl + i, stream);
+                cp_async8_hint(st + kPfStSoh + j * 8, p.soh + i, stream);
 #endif
 #ifndef PF_NOHIST
-            cp_async8_hint(st + kPfStSdeg + j * 8,
-                           p.hist + ((size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)((k & p.Rm) * N)), stream);
+                cp_async8_hint(st + kPfStSdeg + j * 8, hp, stream);
 #endif
 #ifndef PF_NOREC
-            cp_async16_hint(st + kPfStR0 + j * 16, rp, keep);
-            cp_async16_hint(st + kPfStR1 + j * 16, rp + 1, keep);
-            if (n < H) cp_async4_hint(st + kPfStHv + j * 4, p.hdr + (size_t)t1 * p.hdr_stride + n, keep);
-#else
-            (void)rp;
+                cp_async16_hint(st + kPfStR0 + j * 16, rp, keep);
+                cp_async16_hint(st + kPfStR1 + j * 16, rp + 1, keep);
+                if (n < H) cp_async4_hint(st + kPfStHv + j * 4, hd, keep);
 #endif
+            } else {                                          // two vehicles: every copy twice as wide (j, n, i are even)
+                cp_async8_hint(st + kPfStA32 + j * 4, p.actions + i, stream);
+#ifndef PF_NOSTATE
+                cp_async16_hint(st + kPfStSoc + j * 8, p.soc + i, stream);
+                cp_async8_hint(st + kPfStHl + j * 4, p.hl + i, stream);
+                cp_async16_hint(st + kPfStSoh + j * 8, p.soh + i, stream);
+#endif
+#ifndef PF_NOHIST
+                cp_async16_hint(st + kPfStSdeg + j * 8, hp, stream);
+#endif
+#ifndef PF_NOREC
+                cp_async16_hint(st + kPfStR0 + j * 16, rp, keep);
+                cp_async16_hint(st + kPfStR1 + j * 16, rp + 1, keep);
+                cp_async16_hint(st + kPfStR0 + j * 16 + 16, rp + 2, keep);
+                cp_async16_hint(st + kPfStR1 + j * 16 + 16, rp + 3, keep);
+                if (n + 1 < H) cp_async8_hint(st + kPfStHv + j * 4, hd, keep);
+                else if (n < H) cp_async4_hint(st + kPfStHv + j * 4, hd, keep);
+#endif
+            }
+            (void)rp; (void)hp; (void)hd;
         }
         cp_async_commit();
     };
@@ -1475,58 +1560,110 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
         PF_SETTLE();
         PF_MARK(2);
 
-        double q_rew = 0, q_cash = 0, q_ath = 0, q_miss = 0, q_nviol = 0;   // this vehicle's terms of the per-env sums
-        double o_soc = 0, o_sdeg = 0, o_en = 0;                             // new state, stored after the hand-off
-        float o_hl = 0.f;
+        double q_rew = 0, q_cash = 0, q_ath = 0, q_miss = 0, q_nviol = 0;   // these vehicles' terms of the per-env sums
+        double o_soc[kV], o_sdeg[kV], o_en[kV];                             // new state, stored after the hand-off
+        float o_hl[kV];
         size_t o_hist = 0;
+#pragma unroll
+        for (int u = 0; u < kV; u++) { o_soc[u] = 0; o_sdeg[u] = 0; o_en[u] = 0; o_hl[u] = 0.f; }
         if (active) {
             const PfEnv& es = envs[b];
             float* orow = obs_tile + b * D;
             const size_t i = (size_t)tile * cstride + j;
             const int t1 = min(es.t + 1, p.T - 1);
             const int k = es.t - es.t_start;
-            EvRec rec;
-            {
-                const int4 in_r0 = reinterpret_cast<const int4*>(stp + kPfStR0)[j];
-                rec.sr = __hiloint2double(in_r0.y, in_r0.x); rec.tl = __int_as_float(in_r0.z);
-                rec.there = (uint8_t)(in_r0.w & 0xff); rec.there_prev = (uint8_t)((in_r0.w >> 8) & 0xff); rec.pad = 0;
+            // every input of the kV vehicles first (the stage and the observation tile may alias as far as the compiler
+            // knows: loads placed after the observation stores would have to wait for them)
+            EvRec rec[kV];
+            double soh[kV], a[kV];
+            bool flip[kV];
+#pragma unroll
+            for (int u = 0; u < kV; u++) {
+                const int4 in_r0 = reinterpret_cast<const int4*>(stp + kPfStR0)[j + u];
+                const int4 in_r1 = reinterpret_cast<const int4*>(stp + kPfStR1)[j + u];
+                rec[u].sr = __hiloint2double(in_r0.y, in_r0.x); rec[u].tl = __int_as_float(in_r0.z);
+                rec[u].there = (uint8_t)(in_r0.w & 0xff); rec[u].there_prev = (uint8_t)((in_r0.w >> 8) & 0xff); rec[u].pad = 0;
+                rec[u].tt = __int_as_float(in_r1.x); rec[u].cl = __int_as_float(in_r1.y);
+                rec[u].hn = __int_as_float(in_r1.z); rec[u].lax = __int_as_float(in_r1.w);
             }
-            double soc = reinterpret_cast<const double*>(stp + kPfStSoc)[j], sdeg = reinterpret_cast<const double*>(stp + kPfStSdeg)[j];
-            float hl = reinterpret_cast<const float*>(stp + kPfStHl)[j];
-            const double soh = reinterpret_cast<const double*>(stp + kPfStSoh)[j];
-            const bool flip = s_have_flips && p.tflip[i] != 0;
-            const double a = (double)reinterpret_cast<const float*>(stp + kPfStA32)[j];
+            if (kV == 2) {
+                const double2 s2 = *reinterpret_cast<const double2*>(stp + kPfStSoc + j * 8);
+                const double2 d2 = *reinterpret_cast<const double2*>(stp + kPfStSdeg + j * 8);
+                const double2 h2 = *reinterpret_cast<const double2*>(stp + kPfStSoh + j * 8);
+                const float2 l2 = *reinterpret_cast<const float2*>(stp + kPfStHl + j * 4);
+                const float2 a2 = *reinterpret_cast<const float2*>(stp + kPfStA32 + j * 4);
+                o_soc[0] = s2.x; o_soc[kV - 1] = s2.y; o_sdeg[0] = d2.x; o_sdeg[kV - 1] = d2.y;
+                soh[0] = h2.x; soh[kV - 1] = h2.y; o_hl[0] = l2.x; o_hl[kV - 1] = l2.y;
+                a[0] = (double)a2.x; a[kV - 1] = (double)a2.y;
+            } else {
+                o_soc[0] = reinterpret_cast<const double*>(stp + kPfStSoc)[j];
+                o_sdeg[0] = reinterpret_cast<const double*>(stp + kPfStSdeg)[j];
+                soh[0] = reinterpret_cast<const double*>(stp + kPfStSoh)[j];
+                o_hl[0] = reinterpret_cast<const float*>(stp + kPfStHl)[j];
+                a[0] = (double)reinterpret_cast<const float*>(stp + kPfStA32)[j];
+            }
+            float hv0 = 0.f, hv1 = 0.f;
+            if (n < H) hv0 = reinterpret_cast<const float*>(stp + kPfStHv)[j];
+            if (kV == 2 && n + 1 < H) hv1 = reinterpret_cast<const float*>(stp + kPfStHv)[j + 1];
+#pragma unroll
+            for (int u = 0; u < kV; u++) flip[u] = s_have_flips && p.tflip[i + u] != 0;
+#pragma unroll
+            for (int u = 0; u < kV; u++) {
+                double r_rew = 0, r_cash = 0, r_ath = 0, r_miss = 0, r_nviol = 0;
 #ifndef PF_NOMATH
-            ev_slot_step(p, es, i, flip, a, soh, rec.sr, rec.tl, rec.there_prev, soc, hl, sdeg,
-                         q_rew, q_cash, q_ath, q_miss, q_nviol, o_en);
+                ev_slot_step(p, es, i + u, flip[u], a[u], soh[u], rec[u].sr, rec[u].tl, rec[u].there_prev, o_soc[u], o_hl[u],
+                             o_sdeg[u], r_rew, r_cash, r_ath, r_miss, r_nviol, o_en[u]);
 #else  /* diagnostic build: same loads and stores, almost no arithmetic */
-            soc = soc + a * 1e-3; q_rew = a; q_miss = soh; q_ath = a; if (rec.tl != 0.f) hl = rec.tl;
-            if (hl != 0.f) sdeg = soc;
+                o_soc[u] = o_soc[u] + a[u] * 1e-3; r_rew = a[u]; r_miss = soh[u]; r_ath = a[u]; if (rec[u].tl != 0.f) o_hl[u] = rec[u].tl;
+                if (o_hl[u] != 0.f) o_sdeg[u] = o_soc[u];
 #endif
-            o_soc = soc; o_hl = hl; o_sdeg = sdeg;
-            o_hist = (size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)(((k + 1) & p.Rm) * N);
-            {
-                const int4 r1 = reinterpret_cast<const int4*>(stp + kPfStR1)[j];
-                rec.tt = __int_as_float(r1.x); rec.cl = __int_as_float(r1.y);
-                rec.hn = __int_as_float(r1.z); rec.lax = __int_as_float(r1.w);
+                // contributions: the two vehicles of a thread (kV == 2) are added here, even vehicle + odd vehicle
+                if (u == 0) { q_rew = r_rew; q_cash = r_cash; q_ath = r_ath; q_miss = r_miss; q_nviol = r_nviol; }
+                else { q_rew += r_rew; q_cash += r_cash; q_ath += r_ath; q_miss += r_miss; q_nviol += r_nviol; }
             }
-            write_ev_obs<kNorm, kAux>(p, orow, n, soc, hl, rec, flip);
-            // time-only part of the observation: element n of this env's header row (+ the rest when N < H)
-            if (n < H) orow[hpos] = reinterpret_cast<const float*>(stp + kPfStHv)[j];
-            for (int q = n + N; q < H; q += N)
-                orow[q < p.Ha ? 2 * N + q : 2 * N + p.Ha + (kAux ? 5 * N : 0) + (q - p.Ha)] =
-                    ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + q, keep);
+            o_hist = (size_t)(unsigned)tile * p.pf_tile_hist + hist_slot + (unsigned)(((k + 1) & p.Rm) * N);
+            if (wide_obs) {
+                // per-EV observation terms of both vehicles as float2 stores (write_ev_obs for a pair)
+                float4 ax[kV];
+#pragma unroll
+                for (int u = 0; u < kV; u++) {
+                    ax[u] = make_float4(rec[u].tt, rec[u].cl, rec[u].hn, rec[u].lax);
+                    if (flip[u]) ax[u] = aux_on_the_fly<kNorm>(0.9, rec[u].sr, rec[u].tl, rec[u].there, p.lc_batt_cap, p.hn_den, p.max_soc, p.max_hn);
+                }
+                *reinterpret_cast<float2*>(orow + n) = make_float2((float)o_soc[0], (float)o_soc[kV - 1]);
+                *reinterpret_cast<float2*>(orow + N + n) =
+                    kNorm ? make_float2((float)((double)o_hl[0] / p.max_tl), (float)((double)o_hl[kV - 1] / p.max_tl))
+                          : make_float2(o_hl[0], o_hl[kV - 1]);
+                if (kAux) {
+                    float* ao = orow + 2 * N + p.Ha + n;
+                    *reinterpret_cast<float2*>(ao) = make_float2((float)rec[0].there, (float)rec[kV - 1].there);
+                    *reinterpret_cast<float2*>(ao + N) = make_float2(ax[0].x, ax[kV - 1].x);
+                    *reinterpret_cast<float2*>(ao + 2 * N) = make_float2(ax[0].y, ax[kV - 1].y);
+                    *reinterpret_cast<float2*>(ao + 3 * N) = make_float2(ax[0].z, ax[kV - 1].z);
+                    *reinterpret_cast<float2*>(ao + 4 * N) = make_float2(ax[0].w, ax[kV - 1].w);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < kV; u++) write_ev_obs<kNorm, kAux>(p, orow, n + u, o_soc[u], o_hl[u], rec[u], flip[u]);
+            }
+            // time-only part of the observation: elements n (and n+1) of this env's header row (+ the rest when N < H)
+            if (n < H) orow[hpos] = hv0;
+            if (kV == 2 && n + 1 < H) orow[hpos1] = hv1;
+            for (int q = n + N; q < H; q += N) {
+                orow[hdr_pos(q)] = ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + q, keep);
+                if (kV == 2 && q + 1 < H) orow[hdr_pos(q + 1)] = ld_keep_f32(p.hdr + (size_t)t1 * p.hdr_stride + q + 1, keep);
+            }
         }
-        // contributions: with an even N the two vehicles of a lane pair (same env) are added here, even lane + odd lane
-        if (pair) {
+        // kV == 1 with an even N: the two vehicles of a lane pair (same env) are added here, even lane + odd lane
+        if (kV == 1 && pair) {
             q_rew += __shfl_xor_sync(0xffffffffu, q_rew, 1);
             q_cash += __shfl_xor_sync(0xffffffffu, q_cash, 1);
             q_ath += __shfl_xor_sync(0xffffffffu, q_ath, 1);
             q_miss += __shfl_xor_sync(0xffffffffu, q_miss, 1);
             q_nviol += __shfl_xor_sync(0xffffffffu, q_nviol, 1);
         }
-        if (active && !(pair && (j & 1))) {
-            const int cj = pair ? (j >> 1) : j;
+        if (active && (kV == 2 || !(pair && (j & 1)))) {
+            const int cj = (kV == 2) ? tid : (pair ? (j >> 1) : j);
             contrib[Q_REWARD * cslots + cj] = q_rew;
             contrib[Q_CASH * cslots + cj] = q_cash;
             contrib[Q_ATH * cslots + cj] = q_ath;
@@ -1545,14 +1682,25 @@ __global__ void __launch_bounds__(kPfThreads, KPFCTAS) fleet_step_pf_kernel(cons
         if (active) {
 #endif
             const size_t i = (size_t)tile * cstride + j;
+            if (kV == 2) {
 #ifndef PF_NOSTATE
-            __stcs(p.soc + i, o_soc);
-            __stcs(p.hl + i, o_hl);
+                __stcs(reinterpret_cast<double2*>(p.soc + i), make_double2(o_soc[0], o_soc[kV - 1]));
+                __stcs(reinterpret_cast<float2*>(p.hl + i), make_float2(o_hl[0], o_hl[kV - 1]));
 #endif
 #ifndef PF_NOHIST
-            __stcs(p.hist + o_hist, o_sdeg);
+                __stcs(reinterpret_cast<double2*>(p.hist + o_hist), make_double2(o_sdeg[0], o_sdeg[kV - 1]));
 #endif
-            if (kLog) __stcs(p.charge_log + i, o_en);
+                if (kLog) __stcs(reinterpret_cast<double2*>(p.charge_log + i), make_double2(o_en[0], o_en[kV - 1]));
+            } else {
+#ifndef PF_NOSTATE
+                __stcs(p.soc + i, o_soc[0]);
+                __stcs(p.hl + i, o_hl[0]);
+#endif
+#ifndef PF_NOHIST
+                __stcs(p.hist + o_hist, o_sdeg[0]);
+#endif
+                if (kLog) __stcs(p.charge_log + i, o_en[0]);
+            }
         }
         PF_MARK(6);
         issue_copies(tile + kPfStages * G, ev_next, stg);     // refill the stage this tile has just consumed
@@ -1594,7 +1742,7 @@ __device__ __forceinline__ void post_finish_lists(const StepParams& p) {
 }
 
 template <bool kNorm, bool kAux>
-__global__ void __launch_bounds__(kPostThreads, 10) fleet_post_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(kPostThreads, POST_MIN_CTAS) fleet_post_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm_stack = reinterpret_cast<double*>(smem_raw);                    // [rf_S][kPostThreads]
     double* sm_queue = sm_stack + (size_t)p.rf_S * kPostThreads;               // [kRfQueue][kPostThreads]
@@ -1658,7 +1806,7 @@ __global__ void __launch_bounds__(kPostThreads, 10) fleet_post_kernel(const __gr
         PT_MARK(8);
         if (tid == 0 && s_deg != 0)
             atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
-        if (wf & WL_RESET) post_reset_env<kNorm, kAux>(p, e, ev, tid, kPostThreads);
+        if (wf & WL_RESET) { PT_COUNT(13, 1); post_reset_env<kNorm, kAux>(p, e, ev, tid, kPostThreads); PT_MARK(14); }
         else if (tid == 0 && p.rf_on) p.env4[e] = make_int4(ev.x, ev.y, ev.z, k_now);   // samples up to k_now are consumed
         __syncthreads();                                 // everybody has read s_w / s_ent / s_ev / s_deg
         PT_MARK(9);
@@ -1798,6 +1946,67 @@ __global__ void reduce_stats_kernel(const double* stats, double* dst, double pri
         dst[q] = (q == FLEET_S_PENALTY) ? tot[FLEET_S_REWARD] - tot[FLEET_S_CASHFLOW] * price_mult : tot[q];
 }
 
+// ------------------------------------------------------------------------------------------------ device-side log
+// DataLogger.log_data (utils/data_logger/data_logger.py:21-68) for a handful of selected envs: one row per reset
+// (fleet_environment.py:420-432) and per step that does not end the episode (:679-690), kept in a ring in HBM.  Row layout
+// (float64): {ep_count, time index, reward, cashflow, penalties, grid overloading, SOC violation, kind (1 reset row,
+// 2 step row at a daily evaluation, 0 other step row)}, Action[N], Degradation[N], Charging energy[N], SOH[N], Observation[D].
+constexpr int kLogHead = 8;
+struct LogParams {
+    const int* ids;            // [n] logged envs
+    long long* counts;         // [n] rows written so far (ring position = count % rows)
+    double* rows;              // [n][rows][row_doubles]
+    int n, cap, row_doubles;
+};
+
+__global__ void fleet_log_kernel(const StepParams p, const LogParams lg, int after_reset) {
+    const int l = blockIdx.x;
+    const int e = lg.ids[l];
+    const int N = p.N, D = p.D;
+    const int4 ev = p.env4[e];
+    const int k = ev.x - ev.y;
+    int kind;
+    if (after_reset) {
+        if (p.mask && !p.mask[e]) return;
+        kind = 1;
+    } else if (k == 0 && p.auto_reset) kind = 1;                  // finished and auto-reset inside this fleet_step: the finishing
+    else if (k >= p.L) return;                                    // step is not logged (:679), the reset row is
+    else kind = ((p.step_row[min(ev.x, p.T - 1)].flags & TF_TRIGGER) && p.calc_deg) ? 2 : 0;
+    double* row = lg.rows + ((size_t)l * lg.cap + (size_t)(lg.counts[l] % lg.cap)) * lg.row_doubles;
+    const size_t i0 = (size_t)e * N;
+    if (threadIdx.x == 0) {
+        const bool st = kind != 1;
+        const double reward = st ? p.env_f64[(size_t)EF_REWARD64 * p.E + e] : 0.0;
+        const double cash = st ? p.env_f64[(size_t)EF_CASHFLOW * p.E + e] : 0.0;
+        row[0] = (double)ev.z; row[1] = (double)ev.x; row[2] = reward; row[3] = cash;
+        row[4] = st ? reward - cash * p.price_mult : 0.0;                                      // :659
+        row[5] = st ? p.env_f64[(size_t)EF_OVERLOAD * p.E + e] : 0.0;                          // :660
+        row[6] = st ? p.env_f64[(size_t)EF_SOC_VIOL * p.E + e] : 0.0;                          // :661
+        row[7] = (double)kind;
+        // "Charging energy": EvCharger appends charging_energy + discharging_energy, and those two locals survive
+        // from car to car (ev_charger.py:81-82,212): a car's entry carries the last opposite-sign car's energy
+        double last_c = 0, last_d = 0;
+        double* ce = row + kLogHead + 2 * N;
+        for (int n = 0; n < N; n++) {
+            double v = 0;
+            if (st && p.charge_log && p.actions) {
+                const double en = p.charge_log[i0 + n];
+                if (p.actions[i0 + n] >= 0.f) last_c = en; else last_d = en;
+                v = last_c + last_d;
+            }
+            ce[n] = v;
+        }
+    }
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        row[kLogHead + n] = (kind != 1 && p.actions) ? (double)p.actions[i0 + n] : 0.0;
+        row[kLogHead + N + n] = (kind == 2) ? p.last_deg[i0 + n] : 0.0;                        // :665-676
+        row[kLogHead + 3 * N + n] = p.soh[i0 + n];
+    }
+    for (int q = threadIdx.x; q < D; q += blockDim.x) row[kLogHead + 4 * N + q] = p.obs ? (double)p.obs[(size_t)e * D + q] : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) lg.counts[l] += 1;
+}
+
 }  // namespace
 
 // =============================================================================================== host side / C ABI
@@ -1814,7 +2023,7 @@ struct FleetHandle {
     int64_t launches = 0;
     std::string err;
     size_t smem_step = 0, smem_post = 0, smem_pf = 0;
-    int grid_pf = 0, use_pf = 0;
+    int grid_pf = 0, use_pf = 0, pf_v = 1;   // pf_v: vehicles per compute thread of the pf kernel
     int grid = 0, grid_post = 0, need_post = 0, num_sms = 0;
     int max_smem_optin = 0;
     double* charge_log_buf = nullptr;   // fleet_enable_charge_log
@@ -1827,6 +2036,9 @@ struct FleetHandle {
     int timing = 0;
     std::vector<cudaEvent_t> tev;
     int64_t tcount = 0;
+    // device-side DataLogger ring (fleet_enable_log)
+    int* log_ids = nullptr; long long* log_counts = nullptr; double* log_rows = nullptr;
+    int log_n = 0, log_cap = 0, log_row_doubles = 0;
     // host-call staging (fleet_step_host)
     float* h_actions_dev = nullptr; float* h_obs_dev = nullptr; float* h_reward_dev = nullptr; uint8_t* h_done_dev = nullptr;
 };
@@ -1891,14 +2103,16 @@ StepKernel pick_step(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_step_kernel<true, true> : fleet_step_kernel<true, false>;
     return h->c.aux ? fleet_step_kernel<false, true> : fleet_step_kernel<false, false>;
 }
-StepKernel pick_pf(const FleetHandle* h, bool log) {
+template <int kV>
+StepKernel pick_pf_v(const FleetHandle* h, bool log) {
     if (log) {
-        if (h->c.normalize) return h->c.aux ? fleet_step_pf_kernel<true, true, true> : fleet_step_pf_kernel<true, false, true>;
-        return h->c.aux ? fleet_step_pf_kernel<false, true, true> : fleet_step_pf_kernel<false, false, true>;
+        if (h->c.normalize) return h->c.aux ? fleet_step_pf_kernel<true, true, true, kV> : fleet_step_pf_kernel<true, false, true, kV>;
+        return h->c.aux ? fleet_step_pf_kernel<false, true, true, kV> : fleet_step_pf_kernel<false, false, true, kV>;
     }
-    if (h->c.normalize) return h->c.aux ? fleet_step_pf_kernel<true, true, false> : fleet_step_pf_kernel<true, false, false>;
-    return h->c.aux ? fleet_step_pf_kernel<false, true, false> : fleet_step_pf_kernel<false, false, false>;
+    if (h->c.normalize) return h->c.aux ? fleet_step_pf_kernel<true, true, false, kV> : fleet_step_pf_kernel<true, false, false, kV>;
+    return h->c.aux ? fleet_step_pf_kernel<false, true, false, kV> : fleet_step_pf_kernel<false, false, false, kV>;
 }
+StepKernel pick_pf(const FleetHandle* h, bool log) { return h->pf_v == 2 ? pick_pf_v<2>(h, log) : pick_pf_v<1>(h, log); }
 StepKernel pick_post(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_post_kernel<true, true> : fleet_post_kernel<true, false>;
     return h->c.aux ? fleet_post_kernel<false, true> : fleet_post_kernel<false, false>;
@@ -1910,9 +2124,121 @@ StepKernel pick_reset(const FleetHandle* h) {
 
 }  // namespace
 
+static void fleet_log_launch(FleetHandle* h, const StepParams& p, int after_reset, cudaStream_t stream) {
+    LogParams lg;
+    lg.ids = h->log_ids; lg.counts = h->log_counts; lg.rows = h->log_rows;
+    lg.n = h->log_n; lg.cap = h->log_cap; lg.row_doubles = h->log_row_doubles;
+    fleet_log_kernel<<<h->log_n, 128, 0, stream>>>(p, lg, after_reset);
+    h->launches++;
+}
+
+// every device array that makes up the env state, in the order fleet_export_state writes them
+static std::vector<std::pair<void*, size_t>> state_arrays(FleetHandle* h) {
+    const StepParams& p = h->p;
+    const size_t E = (size_t)h->E, EN = E * (size_t)h->N;
+    std::vector<std::pair<void*, size_t>> v;
+    v.push_back({p.env4, E * sizeof(int4)});
+    v.push_back({p.soc, EN * 8}); v.push_back({p.hl, EN * 4}); v.push_back({p.soh, EN * 8});
+    v.push_back({p.hist, EN * (size_t)p.R * 8});
+    v.push_back({p.tflip, EN}); v.push_back({p.n_flips, 4});
+    v.push_back({p.env_f64, (size_t)EF__COUNT * E * 8});
+    v.push_back({p.rf_len, EN * 4}); v.push_back({p.fd_cyc, EN * 8}); v.push_back({p.life, EN * 8});
+    v.push_back({p.n_cycles, EN * 4}); v.push_back({p.last_deg, EN * 8});
+    if (p.rf_on) {
+        v.push_back({p.rf_stack, EN * (size_t)p.rf_S * 8}); v.push_back({p.rf_dc, EN * 4}); v.push_back({p.rf_acc, EN * 16});
+        v.push_back({p.rf_ext, EN * 4});
+        v.push_back({p.ext_owner, (size_t)(p.rf_P > 0 ? p.rf_P : 1) * 4});
+        v.push_back({p.ext_val, (size_t)(p.rf_P > 0 ? p.rf_P : 1) * (size_t)(p.rf_X > 0 ? p.rf_X : 1) * 8});
+    }
+    v.push_back({p.stats, sizeof(double) * kStatStripes * FLEET_S__COUNT});
+    return v;
+}
+struct StateHeader { uint64_t magic; int32_t E, N, R, S, X, P, L, T; };
+constexpr uint64_t kStateMagic = 0x464c54535432ull;   // "FLTST2"
+
 extern "C" {
 
 int fleet_abi_version(void) { return FLEETSTEP_ABI_VERSION; }
+
+int fleet_enable_log(FleetHandle* h, const int32_t* env_ids_host, int32_t n_envs, int32_t rows_per_env) {
+    if (!h) return FLEET_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->log_n) return fail(h, FLEET_E_INVALID, "the log is already enabled on this handle");
+    if (!env_ids_host || n_envs < 1 || rows_per_env < 1) return fail(h, FLEET_E_INVALID, "fleet_enable_log: need env ids, n_envs >= 1 and rows_per_env >= 1");
+    for (int k = 0; k < n_envs; k++)
+        if (env_ids_host[k] < 0 || env_ids_host[k] >= h->E) return fail(h, FLEET_E_INVALID, "fleet_enable_log: env id out of range");
+    int rc;
+    if ((rc = fleet_enable_charge_log(h, 1))) return rc;     // "Charging energy" needs EvCharger's charge_log
+    const int rd = kLogHead + 4 * h->N + h->D;
+    if ((rc = dev_alloc(h, &h->log_ids, (size_t)n_envs))) return rc;
+    if ((rc = dev_alloc(h, &h->log_counts, (size_t)n_envs))) return rc;
+    if ((rc = dev_alloc(h, &h->log_rows, (size_t)n_envs * (size_t)rows_per_env * (size_t)rd))) return rc;
+    CUDA_TRY(h, cudaMemcpy(h->log_ids, env_ids_host, sizeof(int) * (size_t)n_envs, cudaMemcpyHostToDevice));
+    h->log_n = n_envs; h->log_cap = rows_per_env; h->log_row_doubles = rd;
+    return FLEET_OK;
+}
+
+int fleet_log_layout(const FleetHandle* h, int32_t* n_envs, int32_t* rows_per_env, int32_t* row_doubles) {
+    if (!h) return FLEET_E_INVALID;
+    if (n_envs) *n_envs = h->log_n;
+    if (rows_per_env) *rows_per_env = h->log_cap;
+    if (row_doubles) *row_doubles = h->log_row_doubles;
+    return FLEET_OK;
+}
+
+int fleet_read_log(FleetHandle* h, double* rows_host, int64_t* counts_host, void* stream) {
+    if (!h) return FLEET_E_INVALID;
+    if (!h->log_n) return fail(h, FLEET_E_STATE, "fleet_read_log: the log is not enabled (fleet_enable_log)");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t nb = (size_t)h->log_n * (size_t)h->log_cap * (size_t)h->log_row_doubles * 8;
+    if (rows_host) CUDA_TRY(h, cudaMemcpyAsync(rows_host, h->log_rows, nb, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (counts_host) CUDA_TRY(h, cudaMemcpyAsync(counts_host, h->log_counts, sizeof(long long) * (size_t)h->log_n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return FLEET_OK;
+}
+
+int64_t fleet_state_bytes(FleetHandle* h) {
+    if (!h) return 0;
+    size_t n = sizeof(StateHeader);
+    for (auto& a : state_arrays(h)) n += a.second;
+    return (int64_t)n;
+}
+
+int fleet_export_state(FleetHandle* h, void* dst_host, void* stream) {
+    if (!h || !dst_host) return FLEET_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const StepParams& p = h->p;
+    StateHeader hd = {kStateMagic, h->E, h->N, p.R, p.rf_S, p.rf_X, p.rf_P, p.L, p.T};
+    unsigned char* dst = (unsigned char*)dst_host;
+    memcpy(dst, &hd, sizeof hd);
+    size_t off = sizeof hd;
+    for (auto& a : state_arrays(h)) {
+        CUDA_TRY(h, cudaMemcpyAsync(dst + off, a.first, a.second, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        off += a.second;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return FLEET_OK;
+}
+
+int fleet_import_state(FleetHandle* h, const void* src_host, void* stream) {
+    if (!h || !src_host) return FLEET_E_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const StepParams& p = h->p;
+    StateHeader hd;
+    memcpy(&hd, src_host, sizeof hd);
+    if (hd.magic != kStateMagic || hd.E != h->E || hd.N != h->N || hd.R != p.R || hd.S != p.rf_S || hd.X != p.rf_X ||
+        hd.P != p.rf_P || hd.L != p.L || hd.T != p.T)
+        return fail(h, FLEET_E_INVALID, "fleet_import_state: the blob was exported from a handle with a different geometry");
+    const unsigned char* src = (const unsigned char*)src_host;
+    size_t off = sizeof hd;
+    for (auto& a : state_arrays(h)) {
+        CUDA_TRY(h, cudaMemcpyAsync(a.first, src + off, a.second, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        off += a.second;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+    return FLEET_OK;
+}
+
 
 const char* fleet_last_error(const FleetHandle* h) { return h ? h->err.c_str() : "null handle"; }
 
@@ -1934,7 +2260,7 @@ int fleet_enable_charge_log(FleetHandle* h, int32_t enable) {
 
 const char* fleet_step_kernel_name(const FleetHandle* h) {
     if (!h) return "";
-    return h->use_pf ? "fleet_step_pf_kernel" : "fleet_step_kernel";
+    return h->use_pf ? (h->pf_v == 2 ? "fleet_step_pf_kernel<kV=2>" : "fleet_step_pf_kernel<kV=1>") : "fleet_step_kernel";
 }
 
 int fleet_set_timing(FleetHandle* h, int32_t enable) {
@@ -2267,14 +2593,17 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     {
         const char* force = getenv("FLEETSTEP_KERNEL");   // "generic" / "pf"; default: pf when applicable
         const bool want = !force || strcmp(force, "pf") == 0;
-        const int pfB = kPfCompute / N;
+        // two vehicles per compute thread (even N only): FLEETSTEP_PF_V=2
+        h->pf_v = ((N & 1) == 0 && env_int("FLEETSTEP_PF_V", PF_DEFAULT_V) == 2) ? 2 : 1;
+        int pfB = pf_slots(h->pf_v) / N;
+        if (pfB > 32 && h->pf_v == 2) pfB = 32;
         if (want && c.auto_reset && N >= 8 && pfB >= 1 && pfB <= 32) {   // the epilogue warps use one lane per env of a tile
-            const size_t smpf = pf_smem_bytes(pfB, N, h->D);
+            const size_t smpf = pf_smem_bytes(pfB, N, h->D, h->pf_v);
             int per_sm = 0;
             if ((int64_t)smpf <= (int64_t)h->max_smem_optin &&
                 cudaFuncSetAttribute(pick_pf(h, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smpf) == cudaSuccess &&
                 cudaFuncSetAttribute(pick_pf(h, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smpf) == cudaSuccess &&
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_pf(h, true), kPfThreads, smpf) == cudaSuccess && per_sm >= 1) {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_pf(h, true), pf_threads(h->pf_v), smpf) == cudaSuccess && per_sm >= 1) {
                 h->smem_pf = smpf;
                 const int ntiles = (E + pfB - 1) / pfB;
                 p.pf_B = pfB;
@@ -2282,6 +2611,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
                 p.pf_ntiles = ntiles;
                 p.pf_tile_hist = (unsigned int)((size_t)pfB * p.RN);
                 p.pf_pair = (N & 1) ? 0 : 1;
+                p.pf_obs2 = ((h->D & 1) == 0 && (Ha & 1) == 0) ? 1 : 0;
                 p.pf_cslots = pf_contrib_slots(pfB, N);
                 p.pf_cper = p.pf_pair ? N / 2 : N;
                 p.pf_envs_b = (int)align16((size_t)pfB * sizeof(PfEnv));
@@ -2317,6 +2647,7 @@ int fleet_reset(FleetHandle* h, const int32_t* start_idx_dev, const uint8_t* mas
     p.start_idx = start_idx_dev; p.mask = mask_dev; p.obs = obs_dev;
     pick_reset(h)<<<h->grid, kThreads, 0, (cudaStream_t)stream>>>(p);
     h->launches++;
+    if (h->log_n) fleet_log_launch(h, p, 1, (cudaStream_t)stream);
     CUDA_TRY(h, cudaGetLastError());
     return FLEET_OK;
 }
@@ -2332,7 +2663,7 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     cudaEvent_t* tev = nullptr;
     if (h->timing && !h->tev.empty()) tev = &h->tev[(size_t)(h->tcount % kTimingRing) * 3];
     if (tev) cudaEventRecord(tev[0], (cudaStream_t)stream);
-    if (h->use_pf) pick_pf(h, p.charge_log != nullptr)<<<h->grid_pf, kPfThreads, h->smem_pf, (cudaStream_t)stream>>>(p);
+    if (h->use_pf) pick_pf(h, p.charge_log != nullptr)<<<h->grid_pf, pf_threads(h->pf_v), h->smem_pf, (cudaStream_t)stream>>>(p);
     else pick_step(h)<<<h->grid, kThreads, h->smem_step, (cudaStream_t)stream>>>(p);
     h->launches++;
     if (tev) cudaEventRecord(tev[1], (cudaStream_t)stream);
@@ -2341,6 +2672,7 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
         h->launches++;
     }
     if (tev) { cudaEventRecord(tev[2], (cudaStream_t)stream); h->tcount++; }
+    if (h->log_n) { fleet_log_launch(h, p, 0, (cudaStream_t)stream); }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, FLEET_E_CUDA, std::string("fleet_step launch: ") + cudaGetErrorString(e));
     return FLEET_OK;

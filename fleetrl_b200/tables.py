@@ -31,6 +31,32 @@ class FleetInputs:
     building: pd.DataFrame = None          # columns date, load
     pv: pd.DataFrame = None                # columns date, pv
 
+    def csv_round_trip(self) -> "FleetInputs":
+        """The same inputs as the reference would SEE them after schedule.write_reference_csvs: pandas writes floats with
+        repr() and the reference reads them back with read_csv's default (fast, not round-trip exact) float parser, which
+        returns a neighbouring float64 for roughly a quarter of the values (1 ulp).  A fleet built from csv_round_trip()
+        inputs is therefore bit-identical to the one the unmodified reference builds from the written files
+        (tests/test_host_logic.py); the raw in-memory frames give a fleet the reference can never read bit for bit.
+        Only the float columns take the text round trip (dates are exact); PV is parsed by Python's float() in the
+        reference (decimal="," dialect, data_processing.py:357-360), which is exact."""
+        sched = self.schedule.copy()
+        for col in ("Distance_km", "Consumption_kWh", "PowerRating_kW"):
+            sched[col] = _csv_float_round_trip(sched[col].values, ",", ".")
+        price, tariff = self.price.copy(), self.tariff.copy()
+        price["DELU"] = _csv_float_round_trip(price["DELU"].values, ";", ",")
+        tariff["tariff"] = _csv_float_round_trip(tariff["tariff"].values, ";", ",")
+        building = None
+        if self.building is not None:
+            building = self.building.copy()
+            building["load"] = _csv_float_round_trip(building["load"].values, ",", ".")
+        return FleetInputs(sched, price, tariff, building, None if self.pv is None else self.pv.copy())
+
+
+def _csv_float_round_trip(values, sep, decimal):
+    import io
+    txt = pd.DataFrame({"v": np.asarray(values, np.float64), "pad": "x"}).to_csv(index=False, sep=sep, decimal=decimal)
+    return pd.read_csv(io.StringIO(txt), delimiter=sep, decimal=decimal)["v"].to_numpy(np.float64)
+
 
 def read_inputs(rc: _config.ResolvedConfig) -> FleetInputs:
     """CSV dialects of data_processing.py:47,271-280,307,331,357-360."""

@@ -55,8 +55,17 @@ class LazyInfos:
         return (self[i] for i in range(self._n))
 
 
-class FleetVecEnv:
+try:  # pragma: no cover - stable-baselines3 is third party and not part of the build image
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
+except Exception:
+    _VecEnvBase = object
+
+
+class FleetVecEnv(_VecEnvBase):
     """num_envs identical FleetEnvs stepped by one kernel launch pair per step on one GPU.
+
+    When stable-baselines3 is importable this class IS a stable_baselines3 VecEnv (BaseAlgorithm._wrap_env accepts it as
+    is); without it the same protocol is duck-typed.
 
     env_config: dict or JSON path with the reference's keys; `inputs` optionally supplies the schedule / price /
     load / PV frames in memory (synthetic fleets) instead of CSV files under env_config["data_path"].
@@ -75,6 +84,8 @@ class FleetVecEnv:
         self.obs_dim = self.handle.D
         self.observation_space = observation_box(self.obs_dim, bool(c.normalize))
         self.action_space = action_box(self.num_cars)
+        if _VecEnvBase is not object:
+            _VecEnvBase.__init__(self, self.num_envs, self.observation_space, self.action_space)
         self.output = output
         if output not in ("torch", "numpy"):
             raise ValueError("output must be 'torch' or 'numpy'")
@@ -82,7 +93,8 @@ class FleetVecEnv:
         dev = self.device
         self._obs = torch.zeros((E, D), dtype=torch.float32, device=dev)
         self._term = torch.zeros((E, D), dtype=torch.float32, device=dev)
-        self._log_idx, self._log_rows = [], {}
+        self._log_idx = []
+        self._last_done = np.zeros(E, dtype=bool)
         self._night = None          # night-charging window parameters (fleetrl_b200/policies.py), derived on first use
         self._rew = torch.zeros(E, dtype=torch.float32, device=dev)
         self._done = torch.zeros(E, dtype=torch.uint8, device=dev)
@@ -122,15 +134,15 @@ class FleetVecEnv:
         if self.output == "numpy":
             self._h_act.numpy()[...] = np.asarray(a, dtype=np.float32).reshape(E, N)
             self.handle.step_host(self._h_act.numpy(), self._h_obs.numpy(), self._h_rew.numpy(), self._h_done.numpy(), self._term)
-            obs, rew, done = self._h_obs.numpy(), self._h_rew.numpy(), self._h_done.numpy().astype(bool)
+            # fresh arrays like DummyVecEnv / SubprocVecEnv return them: the pinned buffers are overwritten by the next step
+            obs, rew, done = self._h_obs.numpy().copy(), self._h_rew.numpy().copy(), self._h_done.numpy().astype(bool)
             done_idx = np.nonzero(done)[0]
+            self._last_done = done
         else:
             a = torch.as_tensor(a, dtype=torch.float32, device=self.device).reshape(E, N).contiguous()
             self.handle.step(a, self._obs, self._rew, self._done, self._term)
             obs, rew, done = self._obs, self._rew, self._done.bool()
             done_idx = None
-        if self._log_idx:
-            self._log_step_rows(self._actions)
         return obs, rew, done, self._infos(done_idx)
 
     def step(self, actions):
@@ -140,6 +152,8 @@ class FleetVecEnv:
     def _infos(self, done_idx):
         if done_idx is None:   # torch mode: one small D2H of the done flags (use step_raw() to avoid it)
             done_idx = torch.nonzero(self._done).flatten().cpu().numpy()
+            self._last_done = np.zeros(self.num_envs, dtype=bool)
+            self._last_done[done_idx] = True
         if len(done_idx) == 0:
             return LazyInfos(self.num_envs, [], None, None, 0)
         idx_t = torch.as_tensor(done_idx, device=self.device, dtype=torch.long)
@@ -164,56 +178,34 @@ class FleetVecEnv:
     LOG_COLUMNS = ("Episode", "Time", "Observation", "Action", "Reward", "Cashflow", "Penalties", "Grid overloading",
                    "SOC violation", "Degradation", "Charging energy", "SOH")
 
-    def enable_log(self, indices=(0,)):
-        """Record the reference's per-step log rows for the given envs (evaluation runs: a handful of envs; every
-        logged step reads state back from the device).  Rows follow fleet_environment.py:420-432 (reset row) and
-        :679-690 (one row per step that does not end the episode)."""
-        self.handle.enable_charge_log(True)          # "Charging energy" = EvCharger's charge_log (ev_charger.py:212)
+    def enable_log(self, indices=(0,), max_rows=None):
+        """Record the reference's per-step log rows for the given envs (evaluation runs).  The rows are written on the
+        device by the library (fleet_enable_log: a ring of max_rows rows per env, default four episodes) and only read
+        back by get_log; rows follow fleet_environment.py:420-432 (reset row) and :679-690 (one row per step that does
+        not end the episode).  Call it before reset()."""
         self._log_idx = [int(i) for i in self._indices(indices)]
-        self._log_rows = {i: [] for i in self._log_idx}
-        self._log_reset_rows(self._log_idx)
+        L = int(self.built.consts.episode_steps)
+        self.handle.enable_log(self._log_idx, int(max_rows) if max_rows else 4 * L)
 
-    def _log_reset_rows(self, idx):
-        if not idx:
-            return
-        t = self.handle.get("time_idx").cpu().numpy()
-        soh = self.handle.get("soh").cpu().numpy()
-        obs = self._obs.cpu().numpy()
-        N = self.num_cars
-        for i in idx:
-            rows = self._log_rows[i]
-            rows.append({"Episode": len(rows) // int(self.built.consts.episode_steps) + 1,
-                         "Time": pd.Timestamp(self.built.dates[int(t[i])]), "Observation": obs[i].copy(),
-                         "Action": np.zeros(N), "Reward": 0.0, "Cashflow": 0.0, "Penalties": 0.0, "Grid overloading": 0.0,
-                         "SOC violation": 0.0, "Degradation": 0.0, "Charging energy": np.zeros(N), "SOH": soh[i].copy()})
-
-    def _log_step_rows(self, actions):
-        idx = self._log_idx
-        h = self.handle
-        t = h.get("time_idx").cpu().numpy()
-        done = self._done.cpu().numpy().astype(bool)
-        rew, cash = h.get("reward64").cpu().numpy(), h.get("cashflow").cpu().numpy()
-        ovl, viol = h.get("overload").cpu().numpy(), h.get("soc_viol").cpu().numpy()
-        soh, deg = h.get("soh").cpu().numpy(), h.get("last_deg").cpu().numpy()
-        clog = h.get("charge_log").cpu().numpy()
-        obs = self._obs.cpu().numpy()
-        act = actions.detach().cpu().numpy() if torch.is_tensor(actions) else np.asarray(actions)
-        act = act.reshape(self.num_envs, self.num_cars)
-        pm = float(self.built.consts.price_multiplier)
-        hour, minute = self.built.tables["hour"], self.built.tables["minute"]
-        for i in idx:
-            if done[i]:                       # the reference logs nothing for the finishing step; the auto-reset logs its row
-                continue
-            ti = int(t[i])
-            trig = bool(self.built.consts.calc_degradation) and hour[ti] == 14 and minute[ti] == 45
-            rows = self._log_rows[i]
-            rows.append({"Episode": len(rows) // int(self.built.consts.episode_steps) + 1,
-                         "Time": pd.Timestamp(self.built.dates[ti]), "Observation": obs[i].copy(), "Action": act[i].copy(),
-                         "Reward": float(rew[i]), "Cashflow": float(cash[i]), "Penalties": float(rew[i] - cash[i] * pm),
-                         "Grid overloading": float(ovl[i]), "SOC violation": float(viol[i]),
-                         "Degradation": deg[i].copy() if trig else 0.0,
-                         "Charging energy": clog[i].copy(), "SOH": soh[i].copy()})
-        self._log_reset_rows([i for i in idx if done[i]])
+    def _log_frames(self):
+        """DataLogger.log as one DataFrame per logged env (columns LOG_COLUMNS)."""
+        L = int(self.built.consts.episode_steps)
+        frames = {}
+        for rec in self.handle.read_log():
+            first = rec["rows_total"] - len(rec["kind"])          # rows that fell out of the ring
+            rows = []
+            for r in range(len(rec["kind"])):
+                kind = int(rec["kind"][r])
+                rows.append({"Episode": (first + r) // L + 1,                                  # data_logger.py:51
+                             "Time": pd.Timestamp(self.built.dates[int(rec["time_idx"][r])]),
+                             "Observation": rec["obs"][r], "Action": rec["action"][r],
+                             "Reward": float(rec["reward"][r]), "Cashflow": float(rec["cashflow"][r]),
+                             "Penalties": float(rec["penalties"][r]), "Grid overloading": float(rec["overload"][r]),
+                             "SOC violation": float(rec["soc_viol"][r]),
+                             "Degradation": rec["degradation"][r] if kind == 2 else 0.0,
+                             "Charging energy": rec["charging_energy"][r], "SOH": rec["soh"][r]})
+            frames[rec["env"]] = pd.DataFrame(rows, columns=list(self.LOG_COLUMNS))
+        return frames
 
     def baseline_actions(self, policy, out=None):
         """Actions [E, N] (float32, on the device) of one of the reference's rule-based benchmark policies at every env's
@@ -256,10 +248,9 @@ class FleetVecEnv:
 
     # ---- env_method surface of the reference (fleet_environment.py:741-799)
     def _m_is_done(self, idx):
-        t = self.handle.get("time_idx").cpu().numpy()
-        f = self.handle.get("finish_idx").cpu().numpy()
-        last = self._done.cpu().numpy().astype(bool)
-        return [bool(last[i] or t[i] >= f[i]) for i in idx]
+        """episode.done of the step just taken (fleet_environment.py:750); an env that has been auto-reset since is in a
+        new episode, whose own flag is False, but SB3 callers ask right after the step that returned done=True."""
+        return [bool(self._last_done[i]) for i in idx]
 
     def _m_get_time(self, idx):
         t = self.handle.get("time_idx").cpu().numpy()
@@ -290,13 +281,8 @@ class FleetVecEnv:
     def _m_get_log(self, idx):
         """Per-step log of the envs selected with enable_log() in the reference's DataLogger columns; for other envs the
         reduced episode statistics kept on the device (the same quantities summed over envs and steps)."""
-        out = []
-        for i in idx:
-            if i in self._log_rows:
-                out.append(pd.DataFrame(self._log_rows[i], columns=list(self.LOG_COLUMNS)))
-            else:
-                out.append(pd.DataFrame([self.stats()]))
-        return out
+        frames = self._log_frames() if self._log_idx else {}
+        return [frames[i] if i in frames else pd.DataFrame([self.stats()]) for i in idx]
 
     # ---- statistics
     def stats(self, all_reduce=False):
@@ -309,10 +295,21 @@ class FleetVecEnv:
     _STATE_FIELDS = ("soc", "hours_left", "soh", "rf_len", "fd_cyc", "life", "ep_return", "target_soc")
 
     def state_dict(self):
+        """Readable copies of the main state fields plus "blob": the complete device state (history ring, rainflow
+        stacks, counters, statistics) as one opaque array — what load_state_dict restores."""
         d = {k: self.handle.get(k).cpu() for k in self._STATE_FIELDS}
         d["time_idx"] = self.handle.get("time_idx").cpu()
         d["finish_idx"] = self.handle.get("finish_idx").cpu()
+        d["blob"] = torch.from_numpy(self.handle.export_state())
+        d["last_obs"] = self._obs.cpu()
         return d
+
+    def load_state_dict(self, d):
+        """Resume exactly where state_dict() was taken (same env_config and num_envs): the next step() continues the
+        trajectories bit for bit.  Returns the observation the envs were in."""
+        self.handle.import_state(d["blob"].numpy())
+        self._obs.copy_(d["last_obs"].to(self.device))
+        return self._out(self._obs)
 
     def _indices(self, indices):
         if indices is None:

@@ -252,6 +252,26 @@ int fleet_policy_reset(FleetHandle* h, void* stream);
  * 8 bytes of HBM writes per EV-step. */
 int fleet_enable_charge_log(FleetHandle* h, int32_t enable);
 
+/* Device-side DataLogger (utils/data_logger/data_logger.py:21-68, fed at fleet_environment.py:420-432 and :679-690) for a
+ * few selected envs of an evaluation run: after fleet_enable_log every fleet_reset / fleet_step appends the reference's log
+ * row of those envs to a ring of rows_per_env rows per env in HBM (a finishing step is not logged, the reset that follows
+ * is).  A row is row_doubles float64 values: {ep_count, time index, Reward, Cashflow, Penalties, Grid overloading,
+ * SOC violation, kind (1 = reset row, 2 = step with the daily degradation, 0 = other step)}, Action[N], Degradation[N],
+ * Charging energy[N] (with EvCharger's carry-over of the last opposite-sign car, ev_charger.py:81-82,212), SOH[N],
+ * Observation[D].  fleet_read_log copies the rings ([n_envs][rows_per_env][row_doubles]) and the per-env row counts
+ * (ring position = count % rows_per_env) to the host and synchronises. */
+int fleet_enable_log(FleetHandle* h, const int32_t* env_ids_host, int32_t n_envs, int32_t rows_per_env);
+int fleet_log_layout(const FleetHandle* h, int32_t* n_envs, int32_t* rows_per_env, int32_t* row_doubles);
+int fleet_read_log(FleetHandle* h, double* rows_host, int64_t* counts_host, void* stream);
+
+/* Checkpoint / resume: the complete env state of the handle (time indices, SOC, SOH, history ring, rainflow stacks,
+ * degradation members, statistics) as one opaque blob of fleet_state_bytes bytes in host memory.  fleet_import_state only
+ * accepts a blob exported from a handle created with the same configuration and num_envs.  Both synchronise.
+ * Backs FleetVecEnv.state_dict() / load_state_dict(). */
+int64_t fleet_state_bytes(FleetHandle* h);
+int fleet_export_state(FleetHandle* h, void* dst_host, void* stream);
+int fleet_import_state(FleetHandle* h, const void* src_host, void* stream);
+
 const char* fleet_step_kernel_name(const FleetHandle* h);   /* which step kernel fleet_create selected */
 int fleet_set_timing(FleetHandle* h, int32_t enable);
 int fleet_get_timing(FleetHandle* h, double* step_kernel_ms, double* post_kernel_ms, int64_t* steps);

@@ -118,11 +118,28 @@ def extract_tables(env, w0, w1):
     return tb, dates
 
 
+def make_generated_data_path(use_case, n_evs, name, gen_seed):
+    """Scratch input dir holding a fleet from the PRODUCT's generator (fleetrl_b200.schedule) written in the reference's
+    CSV dialects by write_reference_csvs: the BASELINE.json fleet shapes (50-EV lmd / ut, 20-EV ct), which the shipped
+    1-EV schedules cannot provide."""
+    from fleetrl_b200.schedule import generate_schedule, synthetic_series, write_reference_csvs
+    d = tempfile.mkdtemp(prefix="fleet_golden_gen_")
+    sched = generate_schedule(use_case, n_evs, seed=gen_seed)
+    price, tariff, load, pv = synthetic_series(seed=gen_seed + 1)
+    return write_reference_csvs(d, f"{n_evs}_{name}.csv", sched, price, tariff, load, pv)
+
+
 def run_case(name, cfg_over, starts, n_steps_per_ep, action_fn, schedule=None, n_evs=1, linear=False, seed=0,
-             pre_hook=None):
-    """starts: list of start-time strings, one per episode run back to back on the SAME env object."""
+             pre_hook=None, generated=None, log=False):
+    """starts: list of start-time strings, one per episode run back to back on the SAME env object.
+    generated: seed of a fleet from the product's own generator (written to CSV, read by the reference);
+    log: run with log_data=True and keep every DataLogger column (data_logger.py:55-68)."""
     cfg = compat.base_config(**cfg_over)
-    if n_evs > 1 or schedule is not None:
+    if log:
+        cfg["log_data"] = True
+    if generated is not None:
+        cfg.update(make_generated_data_path(cfg["use_case"], n_evs, name, generated))
+    elif n_evs > 1 or schedule is not None:
         src = schedule or cfg["schedule_name"]
         sched_name = f"{n_evs}_{name}.csv"
         cfg["data_path"] = make_data_path(src, n_evs, sched_name)
@@ -182,9 +199,24 @@ def run_case(name, cfg_over, starts, n_steps_per_ep, action_fn, schedule=None, n
     out["start_idx"] = np.array([t - w0 for t in t0s], np.int32)
     out["ep_start_rows"] = np.array(ep_start_rows, np.int32)
     out["n_steps_per_ep"] = np.int32(n_steps_per_ep)
+    if log:
+        lg = env.data_logger.log
+        T0 = dates[w0]
+        step_td = pd.Timedelta(minutes=int(env.time_conf.minutes))
+        out["log_episode"] = lg["Episode"].to_numpy(np.int64)
+        out["log_time_idx"] = np.array([int((pd.Timestamp(t) - T0) / step_td) for t in lg["Time"]], np.int64)
+        out["log_obs"] = np.stack([np.asarray(o, np.float32) for o in lg["Observation"]])
+        out["log_action"] = np.stack([np.asarray(a, np.float64) for a in lg["Action"]])
+        for col, key in (("Reward", "reward"), ("Cashflow", "cashflow"), ("Penalties", "penalties"),
+                         ("Grid overloading", "overload"), ("SOC violation", "soc_viol")):
+            out["log_" + key] = lg[col].to_numpy(np.float64)
+        out["log_degradation"] = np.stack([np.broadcast_to(np.asarray(d, np.float64), (N,)) for d in lg["Degradation"]])
+        out["log_deg_is_array"] = np.array([np.ndim(d) == 1 for d in lg["Degradation"]])
+        out["log_charging_energy"] = np.stack([np.asarray(c, np.float64) for c in lg["Charging energy"]])
+        out["log_soh"] = np.stack([np.asarray(h, np.float64) for h in lg["SOH"]])
     out["consts_json"] = np.array(json.dumps(consts))
     out["meta_json"] = np.array(json.dumps(dict(name=name, cfg={k: v for k, v in cfg.items() if k != "data_path"},
-                                                starts=starts, window=[w0, w1], linear=linear,
+                                                starts=starts, window=[w0, w1], linear=linear, generated=generated,
                                                 numpy=np.__version__, pandas=pd.__version__)))
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, f"{name}.npz")
@@ -206,6 +238,13 @@ def mixed(rng, k, N, env):
     """mostly charge, sometimes idle (exact zeros), sometimes discharge: exercises plateaus in the SOC history"""
     a = rng.uniform(-0.3, 1, N)
     a[rng.random(N) < 0.3] = 0.0
+    return a
+
+
+def mixed_pm(rng, k, N, env):
+    """charging and discharging cars side by side in most steps, some idle"""
+    a = rng.uniform(-1, 1, N)
+    a[rng.random(N) < 0.15] = 0.0
     return a
 
 
@@ -246,6 +285,20 @@ CASES = [
     # used battery: soh <= 0.9 flips target_soc to 0.9 during the first step (fleet_environment.py:613-614)
     dict(name="lmd_5ev_soh09_nodeg", cfg_over=dict(ARBITRAGE, init_soh=0.9, calculate_degradation=False),
          starts=["2020-03-10 06:15"], n_steps_per_ep=96, action_fn=uniform, n_evs=5, seed=10),
+    # ---- BASELINE.json fleet shapes (cfg2 / cfg3 / cfg4): fleets from the product's generator, written to the reference's
+    # CSV dialects (schedule.write_reference_csvs) and read back by the unmodified reference
+    dict(name="cfg2_lmd_50ev_gen", cfg_over=dict(TARIFF, price_name=None, tariff_name=None), starts=["2020-03-10 06:15"],
+         n_steps_per_ep=96, action_fn=uniform, n_evs=50, seed=11, generated=101),
+    dict(name="cfg3_ct_20ev_48h_gen", cfg_over=dict(TARIFF, use_case="ct", episode_length=48, price_name=None, tariff_name=None),
+         starts=["2020-06-08 05:00"], n_steps_per_ep=192, action_fn=uniform, n_evs=20, seed=12, generated=102),
+    dict(name="cfg4_ut_50ev_1h_priceonly_gen",
+         cfg_over=dict(TARIFF, use_case="ut", include_building=False, include_pv=False, episode_length=48, freq="1H",
+                       minutes=60, time_steps_per_hour=1, price_name=None, tariff_name=None),
+         starts=["2020-09-07 03:00"], n_steps_per_ep=48, action_fn=uniform, n_evs=50, seed=13, generated=103),
+    # ---- DataLogger: log_data=True, two episodes on one env object (Episode numbering, reset rows, the 14:45 Degradation
+    # row, EvCharger's charge_log with its car-to-car carry-over, ev_charger.py:81-82,212)
+    dict(name="lmd_5ev_log_two_episodes", cfg_over=dict(ARBITRAGE), starts=["2020-03-02 20:00", "2020-03-03 20:00"],
+         n_steps_per_ep=96, action_fn=mixed_pm, n_evs=5, seed=14, log=True),
 ]
 
 

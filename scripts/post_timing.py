@@ -37,5 +37,6 @@ ent, deg = v[11] / K, v[12] / K
 names = ["-", "stage rows (wait)", "scan", "micro-ops", "stress drains", "evaluation", "write-back", "slow path", "entry total (deg part)",
          "reset + env4"]
 print(f"entries per step {ent:.0f}, with rainflow work {deg:.0f}, micro-op iterations per rainflow warp-pass {v[10] / max(v[12], 1):.1f}")
+print(f"reset entries per step {v[13] / K:.0f}: reset work of thread 0 {v[14] / max(v[13], 1):.0f} cycles per reset entry (mark 8 -> after post_reset_env)")
 for k in range(1, 10):
     print(f"  {names[k]:28s} {v[k] / max(v[11 if k >= 8 else 12], 1):9.0f} cycles per entry")

@@ -22,6 +22,7 @@ class Golden:
         self.meta = json.loads(str(z["meta_json"]))
         self.tables = {k[3:]: z[k] for k in z.files if k.startswith("tb_")}
         self.traj = {k[3:]: z[k] for k in z.files if k.startswith("tr_")}
+        self.log = {k[4:]: z[k] for k in z.files if k.startswith("log_")}     # DataLogger columns (log_data=True cases)
         self.actions = z["actions"]
         self.start_idx = z["start_idx"]
         self.ep_start_rows = z["ep_start_rows"]

@@ -69,3 +69,45 @@ def test_gpu_matches_reference(name):
         np.testing.assert_allclose(o["fd_cyc"], r["fd_cyc"], rtol=1e-12, atol=1e-18)
         np.testing.assert_allclose(o["life"], r["life"], rtol=0, atol=1e-13)
     np.testing.assert_array_equal(o["obs"], r["obs"])
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "_log_" in n])
+def test_gpu_log_matches_reference_datalogger(name):
+    """The device-side log ring (fleet_enable_log) against the reference's own DataLogger frame (log_data=True): every
+    column of data_logger.py:55-68, including the Episode counter, the reset rows, the 14:45 Degradation row and
+    EvCharger's charge_log with its car-to-car carry-over (ev_charger.py:81-82,212)."""
+    from fleetrl_b200._lib import FleetStepHandle
+
+    g = Golden(name)
+    ref = g.log
+    h = FleetStepHandle(g.consts(), g.tables, num_envs=1, device=0)
+    dev = h.device
+    obs = torch.zeros((1, h.D), dtype=torch.float32, device=dev)
+    rew = torch.zeros(1, dtype=torch.float32, device=dev)
+    done = torch.zeros(1, dtype=torch.uint8, device=dev)
+    h.enable_log([0], len(ref["reward"]) + 8)
+    step = 0
+    for ep, t0 in enumerate(g.start_idx):
+        h.reset(start_idx=torch.tensor([int(t0)], dtype=torch.int32, device=dev), obs=obs)
+        for k in range(g.n_steps_per_ep):
+            h.step(torch.from_numpy(g.actions[step][None, :].copy()).to(dev), obs, rew, done)
+            step += 1
+    rec = h.read_log()[0]
+    assert h.check_errors() == 0
+    h.close()
+    n = len(ref["reward"])
+    assert rec["rows_total"] == n == len(rec["kind"])
+    L = g.n_steps_per_ep
+    np.testing.assert_array_equal(np.arange(n) // L + 1, ref["episode"])                 # data_logger.py:51
+    np.testing.assert_array_equal(rec["time_idx"], ref["time_idx"])
+    np.testing.assert_array_equal(rec["obs"], ref["obs"])
+    np.testing.assert_array_equal(rec["action"], ref["action"])
+    np.testing.assert_allclose(rec["reward"], ref["reward"], rtol=1e-11, atol=1e-10)
+    np.testing.assert_allclose(rec["cashflow"], ref["cashflow"], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(rec["penalties"], ref["penalties"], rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(rec["overload"], ref["overload"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(rec["soc_viol"], ref["soc_viol"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(rec["kind"] == 2, ref["deg_is_array"])
+    np.testing.assert_allclose(rec["degradation"], ref["degradation"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(rec["charging_energy"], ref["charging_energy"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(rec["soh"], ref["soh"], rtol=0, atol=1e-13)

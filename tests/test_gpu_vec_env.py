@@ -1,6 +1,7 @@
 """The SB3-shaped FleetVecEnv and the gym-shaped FleetEnv on the GPU, checked against the oracle through the
 public API (synthetic fleet from the product's own generator + table builder)."""
 import numpy as np
+import pandas as pd
 import pytest
 import torch
 
@@ -93,37 +94,127 @@ def test_fleet_env_gym_api():
     env.close()
 
 
-def test_evaluation_log_columns_and_values():
-    """enable_log(): the reference's DataLogger rows (reset row, one row per non-terminal step) for chosen envs."""
+def _carry_over(energy, actions):
+    """EvCharger's charge_log entry is charging_energy + discharging_energy, and those two locals survive from car to car
+    (ev_charger.py:81-82,212): a car's entry includes the last opposite-sign car's energy (pinned against the reference by
+    the log golden, tests/test_gpu_golden.py)."""
+    out, lc, ld = np.zeros(len(energy)), 0.0, 0.0
+    for n in range(len(energy)):
+        if actions[n] >= 0:
+            lc = energy[n]
+        else:
+            ld = energy[n]
+        out[n] = lc + ld
+    return out
+
+
+@pytest.mark.parametrize("output", ["torch", "numpy"])
+def test_evaluation_log_columns_and_values(output):
+    """enable_log(): the reference's DataLogger rows (reset row, one row per non-terminal step) for chosen envs, written
+    by the device-side log ring (fleet_enable_log) in both output modes; every column is checked against the oracle."""
     from fleetrl_b200 import FleetVecEnv
     cfg = default_config("lmd", time_picker="random", end_cutoff=10)
-    E = 8
-    env = FleetVecEnv(cfg, E, inputs=_inputs(), output="torch", env_id_offset=5, seed=3)
+    E, N = 8, 6
+    env = FleetVecEnv(cfg, E, inputs=_inputs(), output=output, env_id_offset=5, seed=3)
     orc = OracleFleet(env.built.consts, env.built.tables, E, env_id_offset=5)
-    env.reset(); orc.reset()
     env.enable_log(indices=[0, 3])
+    env.reset(); o_obs = orc.reset()
+    pm = float(env.built.consts.price_multiplier)
     rng = np.random.default_rng(2)
-    rewards = {0: [], 3: []}
+    want = {i: [dict(kind="reset", obs=o_obs[i].copy(), soh=orc.get("soh")[i].copy())] for i in (0, 3)}
     for s in range(130):
-        a = rng.uniform(-1, 1, (E, 6)).astype(np.float32)
-        env.step(torch.from_numpy(a).to(env.device))
-        _, o_rew, o_cash, o_done, _ = orc.step(a, want_terminal=True)
+        a = rng.uniform(-1, 1, (E, N)).astype(np.float32)
+        a[rng.random((E, N)) < 0.1] = 0.0
+        env.step(a if output == "numpy" else torch.from_numpy(a).to(env.device))
+        o_obs, o_rew, o_cash, o_done, _ = orc.step(a, want_terminal=True)
         for i in (0, 3):
-            if not o_done[i]:
-                rewards[i].append((o_rew[i], o_cash[i]))
+            if o_done[i]:      # the finishing step is not logged; the auto-reset's row is (fleet_environment.py:420-432,679)
+                want[i].append(dict(kind="reset", obs=o_obs[i].copy(), soh=orc.get("soh")[i].copy()))
+            else:
+                want[i].append(dict(kind="step", obs=o_obs[i].copy(), soh=orc.get("soh")[i].copy(), action=a[i].copy(),
+                                    reward=o_rew[i], cash=o_cash[i], overload=orc.get("overload")[i],
+                                    soc_viol=orc.get("soc_viol")[i], time_idx=orc.get("time_idx")[i],
+                                    charge_log=_carry_over(orc.get("charge_log")[i], a[i]), last_deg=orc.get("last_deg")[i].copy()))
     for i in (0, 3):
         log = env.env_method("get_log", indices=[i])[0]
         assert list(log.columns) == list(env.LOG_COLUMNS)
-        steps = log[log["Action"].map(lambda v: np.any(v != 0))]
-        assert len(steps) == len(rewards[i])
-        np.testing.assert_allclose(steps["Reward"].to_numpy(dtype=float), [r for r, _ in rewards[i]], rtol=1e-11, atol=1e-10)
-        np.testing.assert_allclose(steps["Cashflow"].to_numpy(dtype=float), [c for _, c in rewards[i]], rtol=1e-12, atol=1e-13)
-        assert len(log) == len(steps) + 2                 # the initial reset row and the one after the auto-reset
+        assert len(log) == len(want[i]) == 130 + 1          # every step gives one row: its own, or the reset row after a done
         assert log["Episode"].iloc[0] == 1 and log["Episode"].iloc[-1] == 2
-        assert any(np.ndim(d) == 1 for d in log["Degradation"])   # the 14:45 row carries the per-vehicle degradation
-        ce = np.stack(list(steps["Charging energy"]))
-        assert np.isfinite(ce).all() and (ce != 0).any()          # EvCharger's charge_log per vehicle (kWh)
+        n_deg = 0
+        for r, w in enumerate(want[i]):
+            row = log.iloc[r]
+            np.testing.assert_array_equal(row["Observation"], w["obs"], err_msg=f"row {r}")
+            np.testing.assert_allclose(row["SOH"], w["soh"], rtol=0, atol=1e-13)
+            if w["kind"] == "reset":
+                assert row["Reward"] == 0.0 and row["Cashflow"] == 0.0 and row["Penalties"] == 0.0
+                assert not np.any(row["Action"]) and not np.any(row["Charging energy"]) and np.ndim(row["Degradation"]) == 0
+                continue
+            assert row["Time"] == pd.Timestamp(env.built.dates[int(w["time_idx"])])
+            np.testing.assert_array_equal(row["Action"], w["action"].astype(np.float64))
+            np.testing.assert_allclose(row["Reward"], w["reward"], rtol=1e-11, atol=1e-10)
+            np.testing.assert_allclose(row["Cashflow"], w["cash"], rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(row["Penalties"], w["reward"] - w["cash"] * pm, rtol=1e-10, atol=1e-9)   # :659
+            np.testing.assert_allclose(row["Grid overloading"], w["overload"], rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(row["SOC violation"], w["soc_viol"], rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(row["Charging energy"], w["charge_log"], rtol=1e-13, atol=1e-13)
+            if np.ndim(row["Degradation"]) == 1:          # the 14:45 row carries the per-vehicle degradation (:665-676)
+                np.testing.assert_allclose(row["Degradation"], w["last_deg"], rtol=0, atol=1e-13)
+                ts = row["Time"]
+                assert ts.hour == 14 and ts.minute == 45
+                n_deg += 1
+            else:
+                assert row["Degradation"] == 0.0
+        assert n_deg >= 1
     env.close()
+
+
+def test_numpy_outputs_are_fresh_arrays():
+    """SB3 keeps obs_t across env.step (rollout_buffer.add(self._last_obs, ...)): the arrays returned by step() must not be
+    overwritten by the next step (DummyVecEnv / SubprocVecEnv return fresh arrays)."""
+    from fleetrl_b200 import FleetVecEnv
+    cfg = default_config("lmd", time_picker="random", end_cutoff=10)
+    E, N = 16, 6
+    env = FleetVecEnv(cfg, E, inputs=_inputs(), output="numpy", seed=3)
+    env.reset()
+    rng = np.random.default_rng(4)
+    obs1, rew1, done1, _ = env.step(rng.uniform(-1, 1, (E, N)).astype(np.float32))
+    keep = obs1.copy(), rew1.copy(), done1.copy()
+    obs2, rew2, done2, _ = env.step(rng.uniform(-1, 1, (E, N)).astype(np.float32))
+    np.testing.assert_array_equal(obs1, keep[0]); np.testing.assert_array_equal(rew1, keep[1])
+    np.testing.assert_array_equal(done1, keep[2])
+    assert not np.array_equal(obs1, obs2)
+    env.close()
+
+
+def test_state_dict_round_trip_resumes_bit_for_bit():
+    """state_dict() / load_state_dict(): a second env object restored from the checkpoint continues the trajectories of the
+    first one exactly (history ring, rainflow stacks, degradation members, counters and statistics included)."""
+    from fleetrl_b200 import FleetVecEnv
+    cfg = default_config("lmd", time_picker="random", end_cutoff=10)
+    E, N = 32, 6
+    inputs = _inputs()
+    a_env = FleetVecEnv(cfg, E, inputs=inputs, output="torch", env_id_offset=9, seed=3)
+    a_env.reset()
+    rng = np.random.default_rng(6)
+    acts = [torch.from_numpy(rng.uniform(-1, 1, (E, N)).astype(np.float32)).to(a_env.device) for _ in range(260)]
+    for s in range(130):                       # past one episode end and one daily evaluation
+        a_env.step(acts[s])
+    sd = a_env.state_dict()
+    b_env = FleetVecEnv(cfg, E, inputs=inputs, output="torch", env_id_offset=9, seed=3)
+    obs_b = b_env.load_state_dict(sd)
+    np.testing.assert_array_equal(obs_b.cpu().numpy(), a_env._obs.cpu().numpy())
+    for s in range(130, 260):
+        oa, ra, da, _ = a_env.step(acts[s])
+        ob, rb, db, _ = b_env.step(acts[s])
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), f"step {s}"
+    for k in ("soc", "soh", "hours_left", "rf_len", "fd_cyc", "life", "time_idx", "ep_return"):
+        assert torch.equal(a_env.handle.get(k), b_env.handle.get(k)), k
+    sa, sb = a_env.stats(), b_env.stats()
+    for k in sa:
+        assert sa[k] == sb[k], k
+    with pytest.raises(Exception):
+        FleetVecEnv(cfg, E + 1, inputs=inputs, output="torch", seed=3).load_state_dict(sd)
+    a_env.close(); b_env.close()
 
 
 def test_step_host_pageable_and_pinned_agree():

@@ -146,3 +146,33 @@ def test_fleet_cache_roundtrip(tmp_path):
             np.testing.assert_array_equal(back.tables[k], v)
     np.testing.assert_array_equal(back.dates, built.dates)
     assert back.start_ranges == built.start_ranges and back.company == built.company
+
+
+def test_write_reference_csvs_round_trip(tmp_path):
+    """schedule.write_reference_csvs -> tables.read_inputs -> build_fleet gives the same fleet as building it from
+    FleetInputs.csv_round_trip() in memory, bit for bit (the unmodified reference reading those files is pinned by the
+    *_gen goldens, oracle/gen_golden.py); the raw in-memory frames differ from it by at most one ulp per value."""
+    from fleetrl_b200.schedule import write_reference_csvs
+    sched = generate_schedule("ct", 3, start="2020-01-01 00:00", end="2020-02-29 23:59", seed=5)
+    price, tariff, load, pv = synthetic_series(start="2020-01-01 00:00", end="2020-02-29 23:59", seed=6)
+    names = write_reference_csvs(str(tmp_path), "3_ct_gen.csv", sched, price, tariff, load, pv)
+    assert set(os.listdir(tmp_path)) == {"3_ct_gen.csv", "synthetic_spot.csv", "synthetic_tariff.csv", "synthetic_load.csv"}
+    cfg = cfgmod.default_config("ct", end_cutoff=10, **names)
+    from_files = build_fleet(cfg, auto_reset=True)
+    raw = FleetInputs(sched, price, tariff, load, pv)
+    in_memory = build_fleet(cfg, raw.csv_round_trip(), auto_reset=True)
+    assert from_files.consts.to_dict() == in_memory.consts.to_dict()
+    for k, v in from_files.tables.items():
+        if v is None:
+            assert in_memory.tables[k] is None
+        else:
+            np.testing.assert_array_equal(in_memory.tables[k], v, err_msg=k)
+    np.testing.assert_array_equal(from_files.dates, in_memory.dates)
+    unrounded = build_fleet(cfg, raw, auto_reset=True)
+    for k in ("soc_on_return", "delu", "load"):
+        np.testing.assert_allclose(unrounded.tables[k], from_files.tables[k], rtol=1e-13, atol=1e-15, err_msg=k)
+    # the schedule file has the reference's schema (data_processing.py:47-61)
+    import pandas as pd
+    back = pd.read_csv(tmp_path / "3_ct_gen.csv", parse_dates=["date"])
+    assert list(back.columns)[1:] == ["date", "Distance_km", "Consumption_kWh", "Location", "ChargingStation", "ID", "PowerRating_kW"]
+    assert len(back) == len(sched) and set(back["Location"]) == {"home", "driving"}

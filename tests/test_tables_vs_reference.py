@@ -63,3 +63,40 @@ def test_builder_matches_reference_db(name):
     obs, _ = env.reset()
     t0 = int(np.searchsorted(built.dates, np.datetime64(env.episode.time)))
     assert built.start_ranges["static"][0] == t0
+
+
+@pytest.mark.parametrize("name", ["lmd_1ev", "ut_1ev_1h", "ct_1ev"])
+@pytest.mark.parametrize("end_cutoff", [60, 10])
+def test_time_picker_candidate_ranges_match_reference(name, end_cutoff, monkeypatch):
+    """tables.start_index_ranges vs the populations the UNMODIFIED pickers draw from: random_time_picker.py:25-28 and
+    eval_time_picker.py:33-36 (random.choice is intercepted, the candidate DatetimeIndex it receives is compared element
+    by element with dates[lo .. hi])."""
+    import random
+
+    import compat
+    from fleetrl_b200.tables import build_fleet
+
+    cfg = compat.base_config(**{k: v for k, v in CASES[name].items() if not k.startswith("_")})
+    cfg["end_cutoff"] = end_cutoff
+    env = compat.make_reference_env(cfg)
+    from fleetrl.utils.time_picker.eval_time_picker import EvalTimePicker
+    from fleetrl.utils.time_picker.random_time_picker import RandomTimePicker
+
+    built = build_fleet(cfg, auto_reset=False)
+    seen = {}
+
+    def fake_choice(seq):
+        seen["pop"] = seq
+        return seq[0]
+
+    monkeypatch.setattr(random, "choice", fake_choice)
+    for key, picker in (("random", RandomTimePicker()), ("eval", EvalTimePicker(env.time_conf.episode_length))):
+        picker.choose_time(env.db, env.time_conf.freq, env.time_conf.end_cutoff)
+        pop = np.asarray(seen["pop"].values, dtype="datetime64[ns]")
+        lo, hi = built.start_ranges[key]
+        assert hi - lo + 1 == len(pop), f"{key}: {hi - lo + 1} candidates, reference has {len(pop)}"
+        np.testing.assert_array_equal(built.dates[lo:hi + 1].astype("datetime64[ns]"), pop, err_msg=key)
+    # and what reaches the device RNG: the configured picker's range
+    for key in ("random", "eval"):
+        b2 = build_fleet(dict(cfg, time_picker=key), auto_reset=True)
+        assert (b2.consts.start_lo, b2.consts.start_hi) == tuple(built.start_ranges[key])
