@@ -22,7 +22,7 @@ EXPORTS = [
     "fleet_reset", "fleet_step", "fleet_step_host", "fleet_set_next_start", "fleet_get_state", "fleet_set_state",
     "fleet_field_info", "fleet_get_stats", "fleet_reset_stats", "fleet_check_errors", "fleet_launch_count",
     "fleet_device_bytes", "fleet_last_error", "fleet_set_timing", "fleet_get_timing", "fleet_step_kernel_name", "fleet_policy_actions", "fleet_policy_reset", "fleet_enable_charge_log",
-    "fleet_enable_log", "fleet_log_layout", "fleet_read_log", "fleet_state_bytes", "fleet_export_state", "fleet_import_state",
+    "fleet_debug_stress", "fleet_enable_log", "fleet_log_layout", "fleet_read_log", "fleet_state_bytes", "fleet_export_state", "fleet_import_state",
 ]
 
 
@@ -63,6 +63,7 @@ def load_library(path: str = LIB_PATH):
     L.fleet_policy_actions.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.fleet_policy_reset.argtypes = [vp, vp]
     L.fleet_enable_charge_log.argtypes = [vp, i32]
+    L.fleet_debug_stress.argtypes = [vp, vp, vp, i32, vp]
     L.fleet_enable_log.argtypes = [vp, vp, i32, i32]
     L.fleet_log_layout.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.fleet_read_log.argtypes = [vp, vp, vp, vp]

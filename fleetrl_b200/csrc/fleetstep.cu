@@ -127,7 +127,7 @@ struct StepParams {
     unsigned int* err_flags;  // [1]
     const int* next_start;    // [E] or nullptr
     int2* wl;                 // [E] work list of the post kernel: {env, WL_* flags}
-    int* wl_count;            // [4] {entries, next entry to fetch, -, -}
+    int* wl_count;            // [4] {entries pushed from the front, next entry to fetch, entries pushed from the back, -}
     unsigned int* wl_done;    // [1]
     // persistent step kernel geometry (host-computed so that the kernel reads it from the constant bank, not registers)
     int pf_B, pf_bulk, pf_ntiles, pf_cslots, pf_cper, pf_pair;      // pf_B: envs per tile = kPfSlots / N
@@ -342,27 +342,69 @@ constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one wo
 constexpr int kRfBatch = 8;        // history rows in flight per lane while scanning
 constexpr int kRfQueue = 12;       // reversal values queued per lane between two runs of the three-point stack
 #ifndef RF_PEND
-#define RF_PEND 4
-#endif
-#ifndef RF_FLAT
-#define RF_FLAT 64
+#define RF_PEND 12
 #endif
 #ifndef POST_MIN_CTAS
 #define POST_MIN_CTAS 10
 #endif
-constexpr int kRfPend = RF_PEND;   // cycles per lane ...
-constexpr int kRfFlat = RF_FLAT;   // ... and per warp waiting for their stress evaluation (evaluated by the whole warp)
+constexpr int kRfPend = RF_PEND;   // cycles per lane waiting for their stress evaluation (even)
 
-// SEI stress of one cycle: rainflow_sei_degradation.py:68-79 with effective DoD = clip(range*count, 0, 1) (:170)
+// SEI stress of one cycle: rainflow_sei_degradation.py:68-79 with effective DoD = clip(range*count, 0, 1) (:170):
+//     S_dod = 1 / (kd1 * dod ** kd2 + kd3)   (:68)      S_soc = exp(k_sigma * (mean - sigma_ref))   (:70)
+// The post kernel spends most of its FP64 issue slots here (one evaluation per closed cycle and per residue half cycle),
+// so the two transcendental functions are evaluated by short argument-specific series instead of the general-purpose
+// pow / exp (about 60 FP64 instructions instead of 170):
+//   dod ** -0.501 = rsqrt(dod) * exp(-0.001 * ln dod);  ln dod from the exponent and the atanh series of the mantissa in
+//   [sqrt(1/2), sqrt(2)) (|s| <= 0.1716, seven terms: 2e-15 absolute, and it enters multiplied by 0.001); exp(z), 0 <= z <
+//   0.021, as its Taylor polynomial of degree 6 (< 4e-16);  exp(t), |t| <= 0.52, as (Taylor polynomial of degree 9 of
+//   exp(t / 4)) ** 4.  Measured against extended precision over 3.5 M arguments (tests/test_gpu_parity.py::
+//   test_sei_stress_accuracy): relative error below 2e-14, i.e. inside the 1e-12 stated for fd_cyc against the reference.
+// dod < 1e-9 (never seen from SOC histories) takes the general-purpose path; dod == 0 gives exp(+inf) = inf -> stress 0.
 __device__ __forceinline__ double sei_cycle_stress(double range, double count, double mean, double s_temp) {
     const double k_sigma = 1.04, sigma_ref = 0.5, kd1 = 1.4E5, kd2 = -5.01E-1, kd3 = -1.23E5;
     double eff = range * count;
     eff = eff < 0 ? 0 : (eff > 1 ? 1 : eff);
-    // dod ** kd2 as exp(kd2 * log(dod)): a few ulp off a correctly rounded pow (|kd2 log dod| < 20), far inside the
-    // 1e-11 relative tolerance stated for fd_cyc, at a third of the instructions; dod == 0 -> exp(+inf) = inf -> 0
+#ifdef SEI_STRESS_SERIES
+    if (!(eff < 1e-9)) {
+        // ln(eff) = e ln 2 + ln m,  m in [sqrt(1/2), sqrt(2))
+        int hi = __double2hiint(eff);
+        int ex = (hi >> 20) - 1023;
+        double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(eff));
+        if (m > 1.4142135623730951) { m *= 0.5; ex += 1; }
+        const double d = m + 1.0;
+        float r0f;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0f) : "f"((float)d));
+        const double r0 = (double)r0f;
+        const double r = __fma_rn(r0, __fma_rn(-d, r0, 1.0), r0);             // 1 / (m + 1), one Newton step: ~1e-14
+        const double sr = (m - 1.0) * r, w = sr * sr;
+        double pl = __fma_rn(w, 1.0 / 13, 1.0 / 11);
+        pl = __fma_rn(pl, w, 1.0 / 9); pl = __fma_rn(pl, w, 1.0 / 7); pl = __fma_rn(pl, w, 1.0 / 5);
+        pl = __fma_rn(pl, w, 1.0 / 3); pl = __fma_rn(pl, w, 1.0);
+        const double ln = __fma_rn((double)ex, 0.6931471805599453, 2.0 * sr * pl);
+        const double z = (kd2 + 0.5) * ln;                                    // -0.001 ln(eff) in [0, 0.021)
+        double ez = __fma_rn(z, 1.0 / 720, 1.0 / 120);
+        ez = __fma_rn(ez, z, 1.0 / 24); ez = __fma_rn(ez, z, 1.0 / 6); ez = __fma_rn(ez, z, 0.5);
+        ez = __fma_rn(ez, z, 1.0); ez = __fma_rn(ez, z, 1.0);
+        const double s_dod = __drcp_rn(__fma_rn(kd1, rsqrt(eff) * ez, kd3));  // :68
+        const double u = (k_sigma * (mean - sigma_ref)) * 0.25;
+        double eu = __fma_rn(u, 1.0 / 362880, 1.0 / 40320);
+        eu = __fma_rn(eu, u, 1.0 / 5040); eu = __fma_rn(eu, u, 1.0 / 720); eu = __fma_rn(eu, u, 1.0 / 120);
+        eu = __fma_rn(eu, u, 1.0 / 24); eu = __fma_rn(eu, u, 1.0 / 6); eu = __fma_rn(eu, u, 0.5);
+        eu = __fma_rn(eu, u, 1.0); eu = __fma_rn(eu, u, 1.0);
+        eu = eu * eu; eu = eu * eu;                                           // :70
+        return s_dod * eu * s_temp;                                           // :77-79
+    }
+#endif
+    // dod ** kd2 as exp(kd2 * log(dod)): a few ulp off a correctly rounded pow (|kd2 log dod| < 20)
     const double s_dod = 1.0 / (kd1 * exp(kd2 * log(eff)) + kd3);              // :68
     const double s_soc = exp(k_sigma * (mean - sigma_ref));                    // :70
     return s_dod * s_soc * s_temp;                                             // :77-79
+}
+
+// diagnostic: the stress function over arrays (accuracy test)
+__global__ void debug_stress_kernel(const double* eff, const double* mean, double* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sei_cycle_stress(eff[i], 1.0, mean[i], 1.0);
 }
 
 // Claim a stack extension slot for vehicle `vid` (open addressing over the owner table; rare path).
@@ -542,7 +584,7 @@ __device__ __noinline__ double rf_vehicle_slow(const StepParams& p, int e, int n
 //           or gets deeper leaves for rf_vehicle_slow with its HBM state untouched); the top two entries are carried in
 //           registers (t1 = top, t2 = below) together with Y = |t1 - t2| (+inf while there is only one point)
 //   qcol    its column of the reversal queue
-//   flat / myidx   the WARP's list of cycles waiting for their SEI stress, and this lane's indices into it
+//   pcol    its column of cycles {range * count, mean} waiting for their SEI stress
 // The lanes of a warp scan the history rows in lock-step (coalesced loads, eight in flight, branch-free) and queue the
 // reversal values; whenever a queue could overflow, and at the end, the queues are emptied by the three-point stack.
 // The vehicles of a warp have different numbers of reversals and closures, so the stack is cut into micro-operations
@@ -551,17 +593,10 @@ __device__ __noinline__ double rf_vehicle_slow(const StepParams& p, int e, int n
 // run inside that loop: cycles that need them are appended to the warp's list, which all 32 lanes evaluate together
 // (one cycle per lane, whoever owns it); each owner then adds up its own results in list order (deterministic).
 // Returns the SOH loss (0 unless evaluated).
-struct RfWarpBuf {
-    double2* flat;             // [kRfFlat] {range * count, mean} -> .x replaced by the stress
-    unsigned char* myidx;      // [kRfPend][32]
-};
-
 __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, bool active, int k_done, int k_now,
                                              bool evaluate, double s_temp, double* __restrict__ smcol,
-                                             double* __restrict__ qcol, const RfWarpBuf wb) {
+                                             double* __restrict__ qcol, double2* __restrict__ pcol) {
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int N = p.N, S = p.rf_S, Rm = p.Rm;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const size_t i = (size_t)e * N + (active ? n : 0);
@@ -591,37 +626,29 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
     }
     double dsg = live ? x_cur - t1 : 0.0;                    // sign of the last non-zero difference (0: none yet)
     bool big = false;
-    int np = 0, cnt = 0;                                     // this lane's / the warp's cycles waiting for their stress
+    int np = 0;                                              // this lane's cycles waiting for their stress
     bool has_item = false;
     double item_eff = 0, item_mean = 0;
-    // (converged code) append the lanes' new cycles to the warp's list; evaluate the list when it may not take another round
+    // (converged code) a lane's new cycle goes to its own pending column; when a column is full, and at the end, all
+    // lanes evaluate their columns together, two cycles per iteration (two independent log/exp chains in flight), and add
+    // the results up in list order
 #define RF_APPEND(target_)                                                                     \
     do {                                                                                       \
-        const unsigned b_ = __ballot_sync(full, has_item);                                     \
-        if (b_) {                                                                              \
-            if (has_item) {                                                                    \
-                const int idx_ = cnt + __popc(b_ & lt_mask);                                   \
-                wb.flat[idx_] = make_double2(item_eff, item_mean);                             \
-                wb.myidx[np * 32 + lane] = (unsigned char)idx_; np++;                          \
-                has_item = false;                                                              \
-            }                                                                                  \
-            cnt += __popc(b_);                                                                 \
-            if (__any_sync(full, np == kRfPend) || cnt > kRfFlat - 32) RF_DRAIN(target_);      \
-        }                                                                                      \
+        if (has_item) { pcol[np * kPostThreads] = make_double2(item_eff, item_mean); np++; has_item = false; } \
+        if (__any_sync(full, np == kRfPend)) RF_DRAIN(target_);                                \
     } while (0)
 #define RF_DRAIN(target_)                                                                      \
     do {                                                                                       \
-        if (cnt > 0) {                                                                         \
-            __syncwarp();                                                                      \
-            for (int t_ = lane; t_ < cnt; t_ += 32) {                                          \
-                const double2 it_ = wb.flat[t_];                                               \
-                wb.flat[t_].x = sei_cycle_stress(it_.x, 1.0, it_.y, s_temp);                   \
-            }                                                                                  \
-            __syncwarp();                                                                      \
-            for (int k_ = 0; k_ < np; k_++) (target_) += wb.flat[wb.myidx[k_ * 32 + lane]].x;  \
-            np = 0; cnt = 0;                                                                   \
-            __syncwarp();                                                                      \
+        const int m_ = __reduce_max_sync(full, np);                                            \
+        for (int k_ = 0; k_ < m_; k_ += 2) {                                                   \
+            const double2 i0_ = pcol[min(k_, kRfPend - 1) * kPostThreads];                     \
+            const double2 i1_ = pcol[min(k_ + 1, kRfPend - 1) * kPostThreads];                 \
+            const double s0_ = sei_cycle_stress(i0_.x, 1.0, i0_.y, s_temp);                    \
+            const double s1_ = sei_cycle_stress(i1_.x, 1.0, i1_.y, s_temp);                    \
+            if (k_ < np) (target_) += s0_;                                                     \
+            if (k_ + 1 < np) (target_) += s1_;                                                 \
         }                                                                                      \
+        np = 0;                                                                                \
     } while (0)
 
     // ---- committed part: rainflow.reversals + extract_cycles over the pending samples
@@ -790,7 +817,7 @@ __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es
     const double cap = soh * p.cap0;                                // episode.battery_cap[car]
     double c_cr = 0, c_dr = 0, c_inv = 0, c_oc = 0, c_dep = 0, c_cost = 0, c_rev = 0, c_miss = 0, c_nviol = 0;
     double num = 0;                                                 // next_soc = soc + num / cap
-#ifdef EV_BRANCHY
+#ifndef EV_BRANCHFREE
     if (a >= 0) {                                                   // ev_charger.py:98-156
         const double dem = (tgt - soc) * cap;
         const double req = p.P * a * p.dt;
@@ -827,10 +854,11 @@ __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es
         atomicOr(p.err_flags, 1u);                                  // NaN action: TypeError ev_charger.py:209
     }
 #else
-    // The charging (ev_charger.py:98-156) and the discharging (:159-206) branch are both evaluated and the action's sign
-    // selects: in a warp of vehicles with mixed actions both would run anyway, one after the other with half the lanes
-    // masked; written this way their two dependency chains interleave.  Every selected value is produced by exactly the
-    // operations of its branch, so the results are bit-identical to the branching form (-DEV_BRANCHY).
+    // Experiment (-DEV_BRANCHFREE): the charging (ev_charger.py:98-156) and the discharging (:159-206) branch are both
+    // evaluated and the action's sign selects, so that the two dependency chains interleave in a warp of mixed actions.
+    // Every selected value is produced by exactly the operations of its branch (bit-identical, parity suite green), but the
+    // step kernel's time did not move (95.0 vs 95.0 us at cfg2), so the branching form, which skips the unused side when a
+    // policy's actions share a sign, stays the default.
     {
         const bool chg = a >= 0, dis = a < 0, th1 = there == 1;
         const double req = p.P * a * p.dt;
@@ -887,8 +915,15 @@ __device__ __forceinline__ void ev_slot_step(const StepParams& p, const EnvT& es
 // ------------------------------------------------------------------------------------------------ step kernel
 // Work-list entry pushed by the step kernel for envs that need the post kernel (daily degradation and/or reset).
 constexpr int WL_TRIGGER = 1, WL_RESET = 2, WL_FLUSH = 4;
+// Entries with a daily evaluation are by far the longest (consumption + residue stress + fade): they are pushed from the
+// front of the list and fetched first by the post kernel, everything else from the back, so that the kernel does not end
+// with one late-started evaluation.
 __device__ __forceinline__ void wl_push(const StepParams& p, int e, int wf) {
-    p.wl[atomicAdd(p.wl_count, 1)] = make_int2(e, wf);
+    if (wf & WL_TRIGGER) p.wl[atomicAdd(p.wl_count, 1)] = make_int2(e, wf);
+    else p.wl[p.E - 1 - atomicAdd(p.wl_count + 2, 1)] = make_int2(e, wf);
+}
+__device__ __forceinline__ int2 wl_fetch(const StepParams& p, int w, int n_front) {
+    return p.wl[w < n_front ? w : p.E - 1 - (w - n_front)];
 }
 // Work-list flags of an env whose step k (history sample k+1) has just been taken.  WL_FLUSH: with the next sample the
 // ring would hold more than R rows (samples k_done .. k+2), so the pending ones are consumed now.
@@ -1201,6 +1236,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
     return ok != 0;
 }
+// Epilogue-warp variant: the two epilogue warps wait most of a tile period; every failed try costs issue slots the compute
+// warps of the same scheduler could use, so they back off between tries (PF_EPI_SLEEP ns; 0 = plain spin).
+#ifndef PF_EPI_SLEEP
+#define PF_EPI_SLEEP 0
+#endif
+__device__ __forceinline__ void mbar_wait_epi(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+        if (PF_EPI_SLEEP > 0) __nanosleep(PF_EPI_SLEEP);
+    }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     // try_wait suspends the thread for a hardware-defined time before returning false (a __nanosleep back-off here
     // was measured to be 2.4x slower: the hand-offs are on the critical path)
@@ -1282,7 +1327,7 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             const int e0 = tile * B;
             const int nb = min(B, p.E - e0);
             PF_MARK(0);
-            mbar_wait(&bar_done[buf], (uint32_t)((it / kPfOut) & 1));   // the compute warps have written tile `tile`
+            mbar_wait_epi(&bar_done[buf], (uint32_t)((it / kPfOut) & 1));   // the compute warps have written tile `tile`
             PF_SETTLE();
             PF_MARK(1);
 
@@ -1405,7 +1450,7 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             load_env4(tile + 5 * G);
             double ep_prev = 0;                               // episode return so far (lane < nb), fetched ahead of its use
             if (lane < nb) ep_prev = p.env_f64[(size_t)EF_EP_RETURN * p.E + e0 + lane];
-            mbar_wait(&bar_sums_ready[sbuf], (uint32_t)((it >> 1) & 1));   // warp 1 has summed tile `tile`
+            mbar_wait_epi(&bar_sums_ready[sbuf], (uint32_t)((it >> 1) & 1));   // warp 1 has summed tile `tile`
 
             // ---- env-level finalisation: one lane per env
 #ifdef PF_NOEPI
@@ -1737,7 +1782,7 @@ __device__ __forceinline__ void post_finish_lists(const StepParams& p) {
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int d = atomicAdd(p.wl_done, 1u);
-        if (d == gridDim.x - 1) { p.wl_count[0] = 0; p.wl_count[1] = 0; *p.wl_done = 0; }
+        if (d == gridDim.x - 1) { p.wl_count[0] = 0; p.wl_count[1] = 0; p.wl_count[2] = 0; *p.wl_done = 0; }
     }
 }
 
@@ -1746,16 +1791,14 @@ __global__ void __launch_bounds__(kPostThreads, POST_MIN_CTAS) fleet_post_kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm_stack = reinterpret_cast<double*>(smem_raw);                    // [rf_S][kPostThreads]
     double* sm_queue = sm_stack + (size_t)p.rf_S * kPostThreads;               // [kRfQueue][kPostThreads]
-    RfWarpBuf wb;                                                              // per warp
-    wb.flat = reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * kPostThreads) + (threadIdx.x >> 5) * kRfFlat;
-    wb.myidx = reinterpret_cast<unsigned char*>(reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * kPostThreads) +
-                                                (kPostThreads / 32) * kRfFlat) + (threadIdx.x >> 5) * (kRfPend * 32);
+    double2* sm_pend = reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * kPostThreads);   // [kRfPend][kPostThreads]
     __shared__ int s_w;
     __shared__ int2 s_ent;
     __shared__ int4 s_ev;
     __shared__ double s_deg;
     const int tid = threadIdx.x, N = p.N;
-    const int count = p.wl_count[0];
+    const int n_front = p.wl_count[0];
+    const int count = n_front + p.wl_count[2];
     const double temp_ref = 25, k_temp = 6.93E-2;
     const double s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
 
@@ -1763,7 +1806,7 @@ __global__ void __launch_bounds__(kPostThreads, POST_MIN_CTAS) fleet_post_kernel
     // entry's list record and env4 while the current one is processed, so the two dependent round trips are hidden.
     if (tid == 0) {
         s_w = blockIdx.x; s_deg = 0;
-        if (s_w < count) { s_ent = p.wl[s_w]; s_ev = p.env4[s_ent.x]; }
+        if (s_w < count) { s_ent = wl_fetch(p, s_w, n_front); s_ev = p.env4[s_ent.x]; }
     }
     for (;;) {
         __syncthreads();
@@ -1778,7 +1821,7 @@ __global__ void __launch_bounds__(kPostThreads, POST_MIN_CTAS) fleet_post_kernel
         int4 ev_next = make_int4(0, 0, 0, 0);
         if (tid == 0) {
             w_next = atomicAdd(p.wl_count + 1, 1) + (int)gridDim.x;
-            if (w_next < count) { ent_next = p.wl[w_next]; ev_next = p.env4[ent_next.x]; }
+            if (w_next < count) { ent_next = wl_fetch(p, w_next, n_front); ev_next = p.env4[ent_next.x]; }
         }
         PT_START();
         PT_COUNT(11, 1);
@@ -1787,7 +1830,7 @@ __global__ void __launch_bounds__(kPostThreads, POST_MIN_CTAS) fleet_post_kernel
             for (int n0 = 0; n0 < N; n0 += kPostThreads) {   // (all lanes of a warp go in together)
                 const int n = n0 + tid;
                 const double deg = rf_vehicle(p, e, n, n < N, ev.w, k_now, (wf & WL_TRIGGER) != 0, s_temp, sm_stack + tid,
-                                              sm_queue + tid, wb);
+                                              sm_queue + tid, sm_pend + tid);
                 if (deg != 0) atomicAdd(&s_deg, deg);
             }
         } else if (wf & WL_TRIGGER) {                   // EmpiricalDegradation: the last two samples only
@@ -2311,6 +2354,12 @@ int32_t fleet_debug_pf_clk(unsigned long long* out, int32_t reset) {
 #endif
 int64_t fleet_device_bytes(const FleetHandle* h) { return h ? h->bytes : 0; }
 
+int fleet_debug_stress(const double* eff_dev, const double* mean_dev, double* out_dev, int32_t n, void* stream) {
+    if (!eff_dev || !mean_dev || !out_dev || n < 0) return FLEET_E_INVALID;
+    if (n) debug_stress_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(eff_dev, mean_dev, out_dev, n);
+    return cudaGetLastError() == cudaSuccess ? FLEET_OK : FLEET_E_CUDA;
+}
+
 int fleet_destroy(FleetHandle* h) {
     if (!h) return FLEET_E_INVALID;
     cudaSetDevice(h->device);
@@ -2574,7 +2623,7 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     // per-batch reversal lists
     h->num_sms = prop.multiProcessorCount;
     h->need_post = (c.calc_degradation || c.auto_reset) ? 1 : 0;
-    h->smem_post = align16((size_t)(rfS + kRfQueue) * kPostThreads * 8 + (size_t)(kPostThreads / 32) * (kRfFlat * 16 + kRfPend * 32));
+    h->smem_post = align16((size_t)(rfS + kRfQueue + 2 * kRfPend) * kPostThreads * 8);
     if ((int64_t)h->smem_post > (int64_t)h->max_smem_optin) return fail(h, FLEET_E_INVALID, "rf_stack_depth does not fit the post kernel's shared memory");
     {
         int per_sm = 1;

@@ -272,6 +272,11 @@ int64_t fleet_state_bytes(FleetHandle* h);
 int fleet_export_state(FleetHandle* h, void* dst_host, void* stream);
 int fleet_import_state(FleetHandle* h, const void* src_host, void* stream);
 
+/* Diagnostic: the SEI cycle-stress function the post kernel uses (rainflow_sei_degradation.py:68-79 at reference
+ * temperature: 1 / (kd1 * dod**kd2 + kd3) * exp(k_sigma * (mean - sigma_ref))) over device arrays of n effective DoDs and
+ * mean SOCs; backs the accuracy test of its series evaluation. */
+int fleet_debug_stress(const double* eff_dev, const double* mean_dev, double* out_dev, int32_t n, void* stream);
+
 const char* fleet_step_kernel_name(const FleetHandle* h);   /* which step kernel fleet_create selected */
 int fleet_set_timing(FleetHandle* h, int32_t enable);
 int fleet_get_timing(FleetHandle* h, double* step_kernel_ms, double* post_kernel_ms, int64_t* steps);
