@@ -342,10 +342,10 @@ constexpr int kPostThreads = 64;   // threads per CTA of the post kernel (one wo
 constexpr int kRfBatch = 8;        // history rows in flight per lane while scanning
 constexpr int kRfQueue = 12;       // reversal values queued per lane between two runs of the three-point stack
 #ifndef RF_PEND
-#define RF_PEND 12
+#define RF_PEND 8
 #endif
 #ifndef POST_MIN_CTAS
-#define POST_MIN_CTAS 10
+#define POST_MIN_CTAS 8
 #endif
 constexpr int kRfPend = RF_PEND;   // cycles per lane waiting for their stress evaluation (even)
 

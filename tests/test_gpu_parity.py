@@ -193,3 +193,54 @@ def test_sei_stress_accuracy():
     assert got[-1] == 0.0 and want[-1] == 0.0            # dod == 0: no stress
     rel = np.abs(got[:-1] - want[:-1]) / np.abs(want[:-1])
     assert rel.max() < 5e-14, (rel.max(), eff[rel.argmax()])
+
+
+@pytest.mark.parametrize("kernel,n_evs", [("pf", 8), ("generic", 3)])
+def test_year_long_evaluation_episode(kernel, n_evs, monkeypatch):
+    """The reference's evaluation / benchmark callers run ONE episode of n_steps = 8600 hours (agent_eval/
+    basic_evaluation.py:64, benchmarking/uncontrolled_charging.py:45-51): 34,400 quarter-hour steps, 358 daily evaluations
+    over one ever-growing soc_log per vehicle.  The device keeps a 16-row ring and the persistent three-point stack
+    instead of the log; cycle counts must stay bit-exact and SOH within 1e-12 over the whole year."""
+    from fleetrl_b200._lib import FleetStepHandle
+    monkeypatch.setenv("FLEETSTEP_KERNEL", kernel)
+    hours, E = 8600, 2
+    tables, T = make_tables(seed=11, n_evs=n_evs, days=362)
+    consts = make_consts(tables, T, n_evs, episode_hours=hours, use_case="lmd", auto_reset=1 if kernel == "pf" else 0)
+    steps = hours * 4
+    assert consts.episode_steps == steps
+    orc = OracleFleet(consts, tables, E, env_id_offset=3)
+    gpu = FleetStepHandle(consts, tables, E, device=0, env_id_offset=3)
+    assert gpu.device_bytes < 64 << 20                  # no per-episode history on the device
+    dev = gpu.device
+    obs = torch.zeros((E, gpu.D), dtype=torch.float32, device=dev)
+    rew = torch.zeros(E, dtype=torch.float32, device=dev)
+    done = torch.zeros(E, dtype=torch.uint8, device=dev)
+    start = np.zeros(E, np.int32)
+    o_obs = orc.reset(start_idx=start)
+    gpu.reset(start_idx=torch.from_numpy(start).to(dev), obs=obs)
+    np.testing.assert_array_equal(obs.cpu().numpy(), o_obs)
+    rng = np.random.default_rng(3)
+    block = rng.uniform(-1, 1, (steps, E, n_evs)).astype(np.float32)
+    block[:, 0, :] = 1.0                                # env 0: uncontrolled charging (uncontrolled_charging.py:51-54)
+    block[rng.random(block.shape) < 0.1] = 0.0
+    a_dev = torch.from_numpy(block).to(dev)
+    n_eval = 0
+    for s in range(steps):
+        o_obs, o_rew, _, o_done = orc.step(block[s])
+        gpu.step(a_dev[s], obs, rew, done)
+        last = s == steps - 1
+        if s % 96 == 58 or last or s < 200:             # every step at first, then once per day and at the end
+            np.testing.assert_array_equal(done.cpu().numpy(), o_done, err_msg=f"done step {s}")
+            for k in ("time_idx", "rf_len", "n_cycles", "hours_left"):
+                np.testing.assert_array_equal(gpu.get(k).cpu().numpy(), orc.get(k), err_msg=f"{k} step {s}")
+            np.testing.assert_allclose(gpu.get("soh").cpu().numpy(), orc.get("soh"), rtol=0, atol=1e-12, err_msg=f"soh step {s}")
+            np.testing.assert_allclose(gpu.get("fd_cyc").cpu().numpy(), orc.get("fd_cyc"), rtol=1e-10, atol=1e-18)
+            np.testing.assert_allclose(gpu.get("soc").cpu().numpy(), orc.get("soc"), rtol=0, atol=1e-11, err_msg=f"soc step {s}")
+            np.testing.assert_allclose(gpu.get("reward64").cpu().numpy(), o_rew, rtol=1e-11, atol=1e-9)
+            if not last or kernel != "pf":              # (the pf case auto-resets after the last step)
+                np.testing.assert_allclose(obs.cpu().numpy(), o_obs, rtol=0, atol=2e-6, err_msg=f"obs step {s}")
+            n_eval += 1
+    assert o_done.all() and n_eval > 358
+    assert orc.get("n_cycles").max() > 2000             # thousands of cycles per vehicle went through the stack
+    assert gpu.check_errors() == 0 and orc.err_flags() == 0
+    gpu.close()
