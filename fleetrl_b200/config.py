@@ -182,6 +182,11 @@ def resolve(env_config) -> ResolvedConfig:
                                   "KeyError('price_reward_curve') in EvCharger.charge (ev_charger.py:155)")
     if time.freq not in _FREQ_MINUTES or _FREQ_MINUTES[time.freq] != time.minutes:
         raise ValueError(f"freq={time.freq!r} and minutes={time.minutes} disagree or are unsupported")
+    import struct
+    dt = time.minutes / 60
+    if struct.unpack("f", struct.pack("f", dt))[0] != dt:
+        raise ValueError(f"minutes={time.minutes}: the step length {dt} h is not exactly representable in float32 (the device "
+                         "keeps hours_left in float32, exact for 15 / 30 / 60-minute grids); use one of those resolutions")
     return ResolvedConfig(cfg=cfg, ev=ev, score=score, time=time, use_case=use_case)
 
 

@@ -14,6 +14,7 @@ Statistics reproduced
                    Saturday 9±1.5 / 17±1.5 / 75±25; no Sunday; consumption N(0.213,0.1675) kWh/km in
                    [0.0994,0.453], at most 50 kWh per trip; EVSE 11 kW.
   Utility   (ut) : same shape with its own numbers, 5 % Sunday operation (weekend statistics); EVSE 22 kW.
+  Custom         : the delivery pattern with every statistic taken from the env_config's "custom_*" keys.
   Caretaker (ct) : two tours per day around a lunch pause (12:00±15' to 13:30±15' weekdays), operates every day,
                    2 % night emergencies 02:00-04:00 the following night; EVSE 4.7 kW in the file (the env uses 4.6).
 Times snap to the 15-minute grid exactly like the reference (int() of the minute fraction, nearest of 0/15/30/45).
@@ -35,6 +36,27 @@ _STATS = {
 }
 
 
+def _custom_stats(env_config):
+    """ScheduleType.Custom (schedule_config.py:134-172): the delivery pattern (one trip per working day, a shorter
+    Saturday, no Sunday; schedule_generator.py:561-691) with every statistic read from the "custom_*" keys of the
+    env_config, the reference's defaults otherwise."""
+    g = (env_config or {}).get
+    return dict(
+        dep_wd=(g("custom_weekday_departure_time_mean", 7), g("custom_weekday_departure_time_std", 1)),
+        ret_wd=(g("custom_weekday_return_time_mean", 19), g("custom_weekday_return_time_std", 1)),
+        dep_we=(g("custom_weekend_departure_time_mean", 9), g("custom_weekend_departure_time_std", 1.5)),
+        ret_we=(g("custom_weekend_return_time_mean", 17), g("custom_weekend_return_time_std", 1.5)),
+        dist_wd=(g("custom_weekday_distance_mean", 300), g("custom_weekday_distance_std", 25)),
+        dist_we=(g("custom_weekend_distance_mean", 150), g("custom_weekend_distance_std", 25)),
+        min_dist=g("custom_minimum_distance", 20), max_dist=g("custom_max_distance", 400),
+        cons=(g("custom_consumption_mean", 1.3), g("custom_consumption_std", 0.167463672468669),
+              g("custom_minimum_consumption", 0.3994), g("custom_maximum_consumption", 2.5)),
+        clip=g("custom_maximum_consumption_per_trip", 500),
+        min_dep=g("custom_earliest_hour_of_departure", 3), max_dep=g("custom_latest_hour_of_departure", 11),
+        min_ret=g("custom_earliest_hour_of_return", 12), max_ret=g("custom_latest_hour_of_return", 23),
+        power=g("custom_ev_charger_power_in_kw", 120), sunday_prob=0.0)
+
+
 def _snap(time_h, lo=None, hi=None):
     """hour = int(trunc(t)) clipped; minute = nearest of {0,15,30,45} to int(frac*60) (first wins on ties).
     Returns the step-of-day index on the 15-minute grid."""
@@ -46,14 +68,18 @@ def _snap(time_h, lo=None, hi=None):
     return hour * 4 + q
 
 
-def generate_schedule(use_case="lmd", n_evs=1, start="2020-01-01 00:00", end="2020-12-30 23:59", seed=42):
-    """-> DataFrame with the reference schedule columns, stacked by vehicle (ID = 0..n_evs-1), 15-minute grid."""
-    if use_case not in _STATS:
+def generate_schedule(use_case="lmd", n_evs=1, start="2020-01-01 00:00", end="2020-12-30 23:59", seed=42, env_config=None):
+    """-> DataFrame with the reference schedule columns, stacked by vehicle (ID = 0..n_evs-1), 15-minute grid.
+    use_case "custom" takes its statistics from env_config's "custom_*" keys (schedule_config.py:134-172)."""
+    if use_case == "custom":
+        st = _custom_stats(env_config)
+    elif use_case in _STATS:
+        st = _STATS[use_case]
+    else:
         raise TypeError("Company type not found!")
-    st = _STATS[use_case]
     rng = np.random.default_rng(seed)
     dates = pd.date_range(start=start, end=end, freq="15min")
-    if use_case == "lmd":                     # schedule_generator.py:75-86: skip leading Sundays
+    if use_case in ("lmd", "custom"):         # schedule_generator.py:75-86, 572-581: skip leading Sundays
         while dates[0].weekday() == 6:
             dates = dates[96:]
     T = len(dates)
@@ -78,7 +104,7 @@ def generate_schedule(use_case="lmd", n_evs=1, start="2020-01-01 00:00", end="20
                 cons[sl] = (td / n) * rating
                 driving[sl] = True
 
-        if use_case in ("lmd", "ut"):
+        if use_case in ("lmd", "ut", "custom"):
             wd = np.nonzero(day_wd < 5)[0]
             sat = np.nonzero(day_wd == 5)[0]
             sun = np.nonzero((day_wd == 6) & (rng.random(n_days) > 1 - st["sunday_prob"]))[0] if st["sunday_prob"] else np.array([], int)

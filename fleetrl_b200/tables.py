@@ -298,6 +298,20 @@ def build_fleet(env_config, inputs: FleetInputs = None, *, auto_reset=True, carr
     """env_config (dict or JSON path, reference keys) -> FleetConsts + canonical tables."""
     rc = _config.resolve(env_config)
     cfg, ev, sc, tc = rc.cfg, rc.ev, rc.score, rc.time
+    if cfg["gen_schedule"]:
+        # FleetEnv.auto_gen (fleet_environment.py:181,969-992): generate gen_n_evs schedules over gen_start_date ..
+        # gen_end_date, save them as gen_name next to the other inputs and use that file (statistically equivalent fast
+        # generator, fleetrl_b200/schedule.py; with in-memory inputs the generated frame just replaces inputs.schedule)
+        import os
+        from .schedule import generate_schedule
+        sched_gen = generate_schedule(rc.use_case, int(cfg["gen_n_evs"]), cfg["gen_start_date"], cfg["gen_end_date"],
+                                      seed=int(cfg["seed"]), env_config=cfg)
+        if inputs is None:
+            name = cfg["gen_name"] if str(cfg["gen_name"]).endswith(".csv") else str(cfg["gen_name"]) + ".csv"
+            sched_gen.to_csv(os.path.join(cfg["data_path"], name))
+            cfg["schedule_name"] = name
+        else:
+            inputs = FleetInputs(sched_gen, inputs.price, inputs.tariff, inputs.building, inputs.pv)
     if inputs is None:
         inputs = read_inputs(rc)
     sched = inputs.schedule.copy()

@@ -6,7 +6,7 @@ import bench
 from fleetrl_b200._lib import FleetStepHandle
 
 class A: pass
-args = A(); args.use_case="lmd"; args.evs=50; args.episode_hours=24; args.carry=1; args.envs=65536
+args = A(); args.use_case="lmd"; args.evs=50; args.episode_hours=24; args.carry=1; args.cfg=bench.CONFIGS["cfg2"]; args.raw_inputs=True; args.envs=65536
 built = bench.build_workload(args)
 E, N = args.envs, built.consts.num_evs
 h = FleetStepHandle(built.consts, built.tables, E, device=0)

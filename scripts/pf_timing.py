@@ -6,7 +6,7 @@ import bench
 from fleetrl_b200._lib import FleetStepHandle, load_library
 
 class A: pass
-args = A(); args.use_case="lmd"; args.evs=50; args.episode_hours=24; args.carry=1; args.envs=65536
+args = A(); args.use_case="lmd"; args.evs=50; args.episode_hours=24; args.carry=1; args.cfg=bench.CONFIGS["cfg2"]; args.raw_inputs=True; args.envs=65536
 built = bench.build_workload(args)
 E, N = args.envs, built.consts.num_evs
 dev = torch.device("cuda", 0)

@@ -37,7 +37,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     class W: pass
-    w = W(); w.use_case = "lmd"; w.evs = a.evs; w.episode_hours = 24; w.carry = 1
+    w = W(); w.use_case = "lmd"; w.evs = a.evs; w.episode_hours = 24; w.carry = 1; w.cfg = bench.CONFIGS["cfg5"]; w.raw_inputs = True
     built = bench.build_workload(w)
     lo, hi = shard_range(a.total_envs, rank, ws)
     env = FleetVecEnv(None, hi - lo, device=local, env_id_offset=lo, built=built, output="torch")
@@ -57,6 +57,13 @@ def main():
 
     obs = env.reset()
     stream = torch.cuda.current_stream(dev)
+    # de-phase the episodes like bench.py does (env e is e mod L steps into its episode): every rollout step then sees its
+    # share of auto-resets and daily evaluations, the SB3 steady state
+    L = int(built.consts.episode_steps)
+    phase = torch.arange(E, device=dev, dtype=torch.int64) % L
+    for s in range(L):
+        obs, _, _ = env.step_raw(policy(obs))
+        env.handle.reset(mask=(phase == s).to(torch.uint8), obs=env._obs)
     for _ in range(a.warmup):
         obs, _, _ = env.step_raw(policy(obs))
     torch.cuda.synchronize(dev)

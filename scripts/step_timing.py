@@ -6,7 +6,7 @@ import bench
 from fleetrl_b200._lib import FleetStepHandle
 
 class A: pass
-args = A(); args.use_case="lmd"; args.evs=int(os.environ.get("EVS","50")); args.episode_hours=24; args.carry=int(os.environ.get("CARRY","1")); args.envs=int(os.environ.get("ENVS","65536"))
+args = A(); args.use_case="lmd"; args.evs=int(os.environ.get("EVS","50")); args.episode_hours=24; args.carry=int(os.environ.get("CARRY","1")); args.cfg=bench.CONFIGS["cfg2"]; args.raw_inputs=True; args.envs=int(os.environ.get("ENVS","65536"))
 built = bench.build_workload(args)
 if os.environ.get("NODEG"):
     built.consts.calc_degradation = 0

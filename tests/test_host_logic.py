@@ -176,3 +176,36 @@ def test_write_reference_csvs_round_trip(tmp_path):
     back = pd.read_csv(tmp_path / "3_ct_gen.csv", parse_dates=["date"])
     assert list(back.columns)[1:] == ["date", "Distance_km", "Consumption_kWh", "Location", "ChargingStation", "ID", "PowerRating_kW"]
     assert len(back) == len(sched) and set(back["Location"]) == {"home", "driving"}
+
+
+def test_gen_schedule_is_honoured(tmp_path):
+    """env_config["gen_schedule"]=True (fleet_environment.py:181, auto_gen :969-992): gen_n_evs schedules over
+    gen_start_date .. gen_end_date are generated, saved as gen_name in data_path and used instead of schedule_name."""
+    from fleetrl_b200.schedule import write_reference_csvs
+    sched = generate_schedule("lmd", 1, start="2020-01-01 00:00", end="2020-02-29 23:59", seed=5)
+    price, tariff, load, pv = synthetic_series(start="2020-01-01 00:00", end="2020-02-29 23:59", seed=6)
+    names = write_reference_csvs(str(tmp_path), "1_lmd.csv", sched, price, tariff, load, pv)
+    cfg = cfgmod.default_config("lmd", end_cutoff=10, gen_schedule=True, gen_n_evs=3, gen_name="generated",
+                                gen_start_date="2020-01-01 00:00", gen_end_date="2020-02-29 23:59", **names)
+    built = build_fleet(cfg, auto_reset=True)
+    assert os.path.exists(tmp_path / "generated.csv")
+    assert built.consts.num_evs == 3                               # not the 1-EV schedule_name file
+    import pandas as pd
+    gen = pd.read_csv(tmp_path / "generated.csv")
+    assert sorted(gen["ID"].unique()) == [0, 1, 2]
+    # in-memory inputs: the generated frame replaces inputs.schedule
+    b2 = build_fleet(dict(cfg, gen_n_evs=2), FleetInputs(sched, price, tariff, load, pv), auto_reset=True)
+    assert b2.consts.num_evs == 2
+    # custom use case: statistics from the custom_* keys (schedule_config.py:134-172)
+    c3 = cfgmod.default_config("custom", end_cutoff=10, gen_schedule=True, gen_n_evs=2, gen_start_date="2020-01-01 00:00",
+                               gen_end_date="2020-02-29 23:59", custom_ev_battery_size_in_kwh=300, custom_ev_charger_power_in_kw=120,
+                               custom_grid_connection_in_kw=500, custom_weekday_distance_mean=200,
+                               max_batt_cap_in_all_use_cases=300)
+    b3 = build_fleet(c3, FleetInputs(sched, price, tariff, load, pv), auto_reset=True)
+    assert b3.consts.num_evs == 2 and b3.consts.evse_max_power == 120.0 and b3.consts.init_battery_cap == 300
+
+
+def test_unsupported_step_lengths_are_rejected_early():
+    with pytest.raises(ValueError, match="float32"):
+        cfgmod.resolve(cfgmod.default_config("lmd", freq="5min", minutes=5, time_steps_per_hour=12))
+    cfgmod.resolve(cfgmod.default_config("lmd", freq="30min", minutes=30, time_steps_per_hour=2))
