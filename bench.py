@@ -40,10 +40,11 @@ CONFIGS = {
                  label="LMD fleet, 50 EVs, rainflow-SEI degradation, 15-min steps, 24 h episodes, full observer (cfg2)"),
     "cfg3": dict(use_case="ct", evs=20, envs=65536, episode_hours=48, minutes=15, over={},
                  label="caretaker fleet, 20 EVs, building load + PV + grid cap, lunch-break target, rainflow-SEI, 48 h episodes (cfg3)"),
-    "cfg4": dict(use_case="ut", evs=50, envs=65536, episode_hours=48, minutes=60,
-                 over=dict(include_building=False, include_pv=False),
+    "cfg4": dict(use_case="ut", evs=50, envs=65536, episode_hours=48, minutes=60, tariff="fixed",
+                 over=dict(include_building=False, include_pv=False, spot_markup=10, spot_mul=1.5, feed_in_ded=0.25),
                  label="utility fleet, 50 EVs, V2G, spot price + feed-in tariff, 1-hour resolution, price-only observer (cfg4)"),
-    "cfg4full": dict(use_case="ut", evs=50, envs=65536, episode_hours=48, minutes=60, over={},
+    "cfg4full": dict(use_case="ut", evs=50, envs=65536, episode_hours=48, minutes=60, tariff="fixed",
+                     over=dict(spot_markup=10, spot_mul=1.5, feed_in_ded=0.25),
                      label="utility fleet, 50 EVs, V2G, 1-hour resolution, full observer (cfg4 variant)"),
     "cfg5": dict(use_case="lmd", evs=50, total_envs=1048576, episode_hours=24, minutes=15, over={},
                  label="LMD fleet, 50 EVs, 1,048,576 envs sharded over the GPUs (cfg5 env step; the PPO-style rollout "
@@ -69,6 +70,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-envs", type=int, default=2048)
+    ap.add_argument("--actions", default="random", choices=["random", "uncontrolled"],
+                    help="random: U(-1,1) per (env, EV) and step; uncontrolled: a = 1 everywhere (benchmarking/"
+                         "uncontrolled_charging.py:51-54; exercises the overload / overcharging penalty paths, SURVEY 8d cfg2)")
     ap.add_argument("--raw-inputs", action="store_true",
                     help="skip the CSV text round trip of the synthetic inputs (saves ~8 s of start-up; diagnostic runs)")
     ap.add_argument("--settle-episodes", type=int, default=0,
@@ -92,7 +96,7 @@ def build_workload(args):
     from fleetrl_b200.tables import FleetInputs, build_fleet
 
     sched = generate_schedule(args.use_case, args.evs, seed=42)
-    price, tariff, load, pv = synthetic_series(seed=7)
+    price, tariff, load, pv = synthetic_series(seed=7, tariff=args.cfg.get("tariff", "spot"))
     over = dict(args.cfg["over"])
     if args.cfg["minutes"] == 60:
         over.update(freq="1h", minutes=60, time_steps_per_hour=1)
@@ -253,7 +257,7 @@ def workload_config(args, built, D):
     return {"workload": f"{args.cfg['label']}; {args.envs} envs/GPU", "name": args.config,
             "envs_per_gpu": args.envs, "evs": args.evs, "obs_dim": D, "table_len": int(built.consts.table_len),
             "episode_steps": int(built.consts.episode_steps), "auto_reset": True,
-            "carry_degradation_state": bool(args.carry),
+            "carry_degradation_state": bool(args.carry), "actions": getattr(args, "actions", "random"),
             "episode_phase": "de-phased: env e is (e mod episode_steps) steps into its episode when timing starts, so "
                              "every step sees ~E/episode_steps auto-resets and ~E/96 daily evaluations (SB3 steady state)",
             "l2_policy": "per-step working set (actions+state+obs ≈ 0.27 GB at cfg2) exceeds the 126 MB L2; "
@@ -293,6 +297,9 @@ def main():
     done = torch.empty(E, dtype=torch.uint8, device=dev)
     gen = torch.Generator(device=dev); gen.manual_seed(1 + rank)
     ring = [torch.empty((E, N), dtype=torch.float32, device=dev).uniform_(-1, 1, generator=gen) for _ in range(8)]
+    if args.actions == "uncontrolled":
+        for a in ring:
+            a.fill_(1.0)
     h.reset(obs=obs)
     torch.cuda.synchronize(dev)
 

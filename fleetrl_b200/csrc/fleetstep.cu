@@ -129,6 +129,8 @@ struct StepParams {
     int2* wl;                 // [E] work list of the post kernel: {env, WL_* flags}
     int* wl_count;            // [4] {entries pushed from the front, next entry to fetch, entries pushed from the back, -}
     unsigned int* wl_done;    // [1]
+    int* wl_chunks;           // [E] per work-list entry: chunks of it that have finished (self-clearing), or nullptr
+    int post_chunks, post_cv; // post kernel: work items per entry, vehicles per item
     // persistent step kernel geometry (host-computed so that the kernel reads it from the constant bank, not registers)
     int pf_B, pf_bulk, pf_ntiles, pf_cslots, pf_cper, pf_pair;      // pf_B: envs per tile = kPfSlots / N
     int pf_obs2;                                              // D and Ha are even: a vehicle pair's observation terms are 8-byte aligned
@@ -593,6 +595,7 @@ __device__ __noinline__ double rf_vehicle_slow(const StepParams& p, int e, int n
 // run inside that loop: cycles that need them are appended to the warp's list, which all 32 lanes evaluate together
 // (one cycle per lane, whoever owns it); each owner then adds up its own results in list order (deterministic).
 // Returns the SOH loss (0 unless evaluated).
+template <int kT>
 __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, bool active, int k_done, int k_now,
                                              bool evaluate, double s_temp, double* __restrict__ smcol,
                                              double* __restrict__ qcol, double2* __restrict__ pcol) {
@@ -612,7 +615,7 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
         x_cur = __ldcs(hcol + (size_t)(k_done & Rm) * N);
         for (int s = 0; s < S; s += 2) {                     // (S is even; entries >= depth are don't-cares)
             const double2 v2 = *reinterpret_cast<const double2*>(stk + s);
-            smcol[s * kPostThreads] = v2.x; smcol[(s + 1) * kPostThreads] = v2.y;
+            smcol[s * kT] = v2.x; smcol[(s + 1) * kT] = v2.y;
         }
         depth = (int)(dc & 0xffffu); c = (int)(dc >> 16);
     }
@@ -621,8 +624,8 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
     PT_START();
     double t1 = 0, t2 = 0, Y = inf;
     if (live) {
-        t1 = smcol[(depth - 1) * kPostThreads];
-        if (depth >= 2) { t2 = smcol[(depth - 2) * kPostThreads]; Y = fabs(t1 - t2); }
+        t1 = smcol[(depth - 1) * kT];
+        if (depth >= 2) { t2 = smcol[(depth - 2) * kT]; Y = fabs(t1 - t2); }
     }
     double dsg = live ? x_cur - t1 : 0.0;                    // sign of the last non-zero difference (0: none yet)
     bool big = false;
@@ -634,15 +637,15 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
     // the results up in list order
 #define RF_APPEND(target_)                                                                     \
     do {                                                                                       \
-        if (has_item) { pcol[np * kPostThreads] = make_double2(item_eff, item_mean); np++; has_item = false; } \
+        if (has_item) { pcol[np * kT] = make_double2(item_eff, item_mean); np++; has_item = false; } \
         if (__any_sync(full, np == kRfPend)) RF_DRAIN(target_);                                \
     } while (0)
 #define RF_DRAIN(target_)                                                                      \
     do {                                                                                       \
         const int m_ = __reduce_max_sync(full, np);                                            \
         for (int k_ = 0; k_ < m_; k_ += 2) {                                                   \
-            const double2 i0_ = pcol[min(k_, kRfPend - 1) * kPostThreads];                     \
-            const double2 i1_ = pcol[min(k_ + 1, kRfPend - 1) * kPostThreads];                 \
+            const double2 i0_ = pcol[min(k_, kRfPend - 1) * kT];                     \
+            const double2 i1_ = pcol[min(k_ + 1, kRfPend - 1) * kT];                 \
             const double s0_ = sei_cycle_stress(i0_.x, 1.0, i0_.y, s_temp);                    \
             const double s1_ = sei_cycle_stress(i1_.x, 1.0, i1_.y, s_temp);                    \
             if (k_ < np) (target_) += s0_;                                                     \
@@ -666,7 +669,7 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
                 //   X >= Y, two points    Y contains the starting point: half cycle (t2, t1), popleft, (t2, t1) <- (t1, v), Y <- X
                 //   X >= Y, more points   full cycle (t2, t1): discard its peak and valley, refill (t2, t1) from the copy; v stays
                 const bool act = q < nq;
-                const double v = qcol[min(q, kRfQueue - 1) * kPostThreads];
+                const double v = qcol[min(q, kRfQueue - 1) * kT];
                 const double X = fabs(v - t1);
                 const bool lt = X < Y, two = depth == 2;
                 const bool closing = act && !lt;
@@ -681,9 +684,9 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
                     item_eff = two ? 0.5 * Y : Y; item_mean = mean;
                     big = big || (closing && Y > 5);
                     c += closing ? 1 : 0;
-                    if (push) smcol[max(depth - 2, 0) * kPostThreads] = t2;
+                    if (push) smcol[max(depth - 2, 0) * kT] = t2;
                     depth += push ? 1 : (full_c ? -2 : 0);
-                    const double s1 = smcol[max(depth - 1, 0) * kPostThreads], s2 = smcol[max(depth - 2, 0) * kPostThreads];
+                    const double s1 = smcol[max(depth - 1, 0) * kT], s2 = smcol[max(depth - 2, 0) * kT];
                     t2 = consume ? t1 : (full_c ? s2 : t2);
                     t1 = consume ? v : (full_c ? s1 : t1);
                     Y = consume ? X : (full_c ? (depth >= 2 ? fabs(t1 - t2) : inf) : Y);
@@ -705,7 +708,7 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
         for (int u = 0; u < kRfBatch; u++) {
             const double d = xb[u] - x_cur;
             const bool flip = live && (dsg * d < 0);
-            if (flip) { qcol[nq * kPostThreads] = x_cur; nq++; }
+            if (flip) { qcol[nq * kT] = x_cur; nq++; }
             dsg = (d != 0) ? d : dsg;
             x_cur = live ? xb[u] : x_cur;
         }
@@ -713,7 +716,7 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
     RF_DRAIN(acc.y);
     PT_MARK(4);
     // the top two entries go back to the stack copy
-    if (live) { smcol[(depth - 1) * kPostThreads] = t1; if (depth >= 2) smcol[(depth - 2) * kPostThreads] = t2; }
+    if (live) { smcol[(depth - 1) * kT] = t1; if (depth >= 2) smcol[(depth - 2) * kT] = t2; }
 
     // ---- evaluation: the provisional end point x_cur on a READ-ONLY view stack[lo .. h) of the committed points
     double deg = 0;
@@ -726,7 +729,7 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
             if (phase == 0) {
                 bool closed = false;
                 if (h - lo >= 2) {
-                    const double x2 = smcol[(h - 1) * kPostThreads], x1 = smcol[(h - 2) * kPostThreads];
+                    const double x2 = smcol[(h - 1) * kT], x1 = smcol[(h - 2) * kT];
                     const double yy = fabs(x2 - x1);
                     if (!(fabs(x_cur - x2) < yy)) {
                         closed = true;
@@ -741,7 +744,7 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
             } else if (phase == 1) {
                 // "count the remaining ranges as one-half cycles", bottom first; the last of them is list position m-1,
                 // which the slice [rainflow_length-1 : len-1] never includes
-                const double xa = smcol[k * kPostThreads], xb2 = (k + 1 < h) ? smcol[(k + 1) * kPostThreads] : x_cur;
+                const double xa = smcol[k * kT], xb2 = (k + 1 < h) ? smcol[(k + 1) * kT] : x_cur;
                 const double mean = 0.5 * (xa + xb2);
                 msum += mean;
                 if (k + 1 < h) {
@@ -765,7 +768,7 @@ __device__ __forceinline__ double rf_vehicle(const StepParams& p, int e, int n, 
     PT_MARK(5);
     if (live) {
         for (int s = 0; s < S; s += 2)
-            *reinterpret_cast<double2*>(stk + s) = make_double2(smcol[s * kPostThreads], smcol[(s + 1) * kPostThreads]);
+            *reinterpret_cast<double2*>(stk + s) = make_double2(smcol[s * kT], smcol[(s + 1) * kT]);
         p.rf_dc[i] = (unsigned int)depth | ((unsigned int)c << 16);
         p.rf_acc[i] = acc;
     }
@@ -795,6 +798,17 @@ __device__ __forceinline__ void bulk_store_s2g_nofence(void* gdst, const void* s
                  :: "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
 #endif
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// One thread sends nfl floats from shared to global memory where source and destination have the SAME offset inside a
+// 16-byte line (the pf kernel lays its observation tile out with the phase of its destination): up to three scalar head
+// floats, one bulk store for the 16-byte aligned middle, up to three scalar tail floats.  Any D and any tile size.
+__device__ __forceinline__ void thread_store_range(float* gdst, const float* ssrc, int nfl) {
+    int head = (int)(((16u - (unsigned)((uintptr_t)gdst & 15u)) & 15u) >> 2);
+    head = head < nfl ? head : nfl;
+    const int mid = (nfl - head) & ~3;
+    for (int k = 0; k < head; k++) gdst[k] = ssrc[k];
+    if (mid > 0) bulk_store_s2g_nofence(gdst + head, ssrc + head, (uint32_t)mid * 4u);
+    for (int k = head + mid; k < nfl; k++) gdst[k] = ssrc[k];
 }
 __device__ __forceinline__ void bulk_store_wait_read() {
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1212,7 +1226,7 @@ constexpr int kPfEnvs = 4;    // env-scratch buffers: staged three tiles ahead
 __host__ __device__ inline int pf_contrib_slots(int B, int N) { return (N & 1) ? B * N : (B * N) / 2; }
 __host__ __device__ inline size_t pf_smem_bytes(int B, int N, int D, int kV) {
     return align16(kPfEnvs * align16((size_t)B * sizeof(PfEnv)) + kPfOut * align16((size_t)kNQ * pf_contrib_slots(B, N) * 8) +
-                   2 * align16((size_t)kNQ * B * 8) + kPfOut * align16((size_t)B * D * 4)) + (size_t)kPfStages * pf_stage_bytes(kV);
+                   2 * align16((size_t)kNQ * B * 8) + kPfOut * align16((size_t)B * D * 4 + 12)) + (size_t)kPfStages * pf_stage_bytes(kV);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
@@ -1322,7 +1336,8 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             const int buf = it % kPfOut, sbuf = it & 1;
             const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + (it % kPfEnvs) * p.pf_envs_b);
             const double* contrib = reinterpret_cast<const double*>(contrib0 + buf * p.pf_contrib_b);
-            const float* obs_tile = reinterpret_cast<const float*>(obs0 + buf * p.pf_obs_b);
+            // the tile sits in shared memory at the 16-byte phase of its destination obs + e0 * D (0 when B * D % 4 == 0)
+            const float* obs_tile = reinterpret_cast<const float*>(obs0 + buf * p.pf_obs_b) + (int)(((size_t)tile * (size_t)(B * D)) & 3);
             double* sums_w = sums + sbuf * sums_stride;
             const int e0 = tile * B;
             const int nb = min(B, p.E - e0);
@@ -1336,15 +1351,16 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             if (use_bulk) {
                 // the writers have run fence.proxy.async before arriving on bar_done: no second fence here
 #ifndef PF_NOOBS
-                if (lane == 0) bulk_store_s2g_nofence(p.obs + (size_t)e0 * D, obs_tile, (uint32_t)(B * D * 4));
+                if (lane == 0) thread_store_range(p.obs + (size_t)e0 * D, obs_tile, B * D);
 #endif
-            } else if (p.pf_bulk && (D & 3) == 0) {
-                // rows of finishing envs go to terminal_obs: one bulk store per env row (D*4 bytes, 16-byte aligned)
+            } else if (p.pf_bulk) {
+                // rows of finishing envs go to terminal_obs: one bulk store per env row (row e has the same 16-byte phase
+                // in obs, in terminal_obs and in the tile)
                 if (lane < nb) {
                     const int e = e0 + lane;
                     float* dst = (envs[lane].flags & EF_RESET) ? (p.terminal_obs ? p.terminal_obs + (size_t)e * D : nullptr)
                                                                : (p.obs ? p.obs + (size_t)e * D : nullptr);
-                    if (dst) bulk_store_s2g_nofence(dst, obs_tile + (size_t)lane * D, (uint32_t)(D * 4));
+                    if (dst) thread_store_range(dst, obs_tile + (size_t)lane * D, D);
                 }
             } else {
                 for (int w = lane; w < nb * D; w += 32) {
@@ -1376,7 +1392,7 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_sums_ready[sbuf]);
             PF_MARK(2);
-            if (p.pf_bulk && (use_bulk ? lane == 0 : (lane < nb && (D & 3) == 0))) bulk_store_wait_read();
+            if (p.pf_bulk && (use_bulk ? lane == 0 : lane < nb)) bulk_store_wait_read();
             __syncwarp();
             PF_MARK(3);
             if (lane == 0) mbar_arrive(&bar_free[buf]);       // contribution + obs buffers of this tile are free again
@@ -1587,7 +1603,7 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
     for (int tile = tile0; tile < ntiles; tile += G, it++) {
         const PfEnv* envs = reinterpret_cast<const PfEnv*>(envs0 + ebuf * p.pf_envs_b);
         double* contrib = reinterpret_cast<double*>(contrib0 + buf * p.pf_contrib_b);
-        float* obs_tile = reinterpret_cast<float*>(obs0 + buf * p.pf_obs_b);
+        float* obs_tile = reinterpret_cast<float*>(obs0 + buf * p.pf_obs_b) + (int)(((size_t)tile * (size_t)(B * D)) & 3);
         const int e0 = tile * B;
         const int nb = min(B, p.E - e0);
         const bool active = slot && b < nb;
@@ -1765,18 +1781,6 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
 //   WL_FLUSH    is about to wrap its history ring: consume the pending samples (no evaluation);
 //   WL_RESET    finished its episode with auto-reset on: FleetEnv.reset (:330-434) AFTER the evaluation, i.e. the order in
 //               which a SubprocVecEnv worker runs them.
-// Auto-reset of one finished env by `nthr` cooperating threads (rank `tid`): FleetEnv.reset as the SubprocVecEnv
-// worker calls it right after a done step.  `ev` is the env's {t, t_start, ep_count} before the reset.
-template <bool kNorm, bool kAux>
-__device__ __forceinline__ void post_reset_env(const StepParams& p, int e, int4 ev, int tid, int nthr) {
-    const int t0 = p.next_start ? p.next_start[e] : draw_start(p.seed, p.start_lo, p.start_hi, p.env_id_offset + e, ev.z);
-    for (int n = tid; n < p.N; n += nthr)
-        reset_slot<kNorm, kAux>(p, e, n, t0, p.obs ? p.obs + (size_t)e * p.D : nullptr, !p.carry);
-    if (tid == 0) {
-        p.env4[e] = make_int4(t0, t0, ev.z + 1, 0);
-        p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = 0;
-    }
-}
 // The last CTA of a post kernel to finish clears the work list for the next step.
 __device__ __forceinline__ void post_finish_lists(const StepParams& p) {
     if (threadIdx.x == 0) {
@@ -1786,12 +1790,13 @@ __device__ __forceinline__ void post_finish_lists(const StepParams& p) {
     }
 }
 
-template <bool kNorm, bool kAux>
-__global__ void __launch_bounds__(kPostThreads, POST_MIN_CTAS) fleet_post_kernel(const __grid_constant__ StepParams p) {
+// kT = threads per CTA = lanes per work item: 32 (default: one warp per item) or 64 (FLEETSTEP_POST_THREADS=64: two warps)
+template <bool kNorm, bool kAux, int kT>
+__global__ void __launch_bounds__(kT, kT == 32 ? 2 * POST_MIN_CTAS : POST_MIN_CTAS) fleet_post_kernel(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sm_stack = reinterpret_cast<double*>(smem_raw);                    // [rf_S][kPostThreads]
-    double* sm_queue = sm_stack + (size_t)p.rf_S * kPostThreads;               // [kRfQueue][kPostThreads]
-    double2* sm_pend = reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * kPostThreads);   // [kRfPend][kPostThreads]
+    double* sm_stack = reinterpret_cast<double*>(smem_raw);                    // [rf_S][kT]
+    double* sm_queue = sm_stack + (size_t)p.rf_S * kT;               // [kRfQueue][kT]
+    double2* sm_pend = reinterpret_cast<double2*>(sm_queue + (size_t)kRfQueue * kT);   // [kRfPend][kT]
     __shared__ int s_w;
     __shared__ int2 s_ent;
     __shared__ int4 s_ev;
@@ -1802,55 +1807,80 @@ __global__ void __launch_bounds__(kPostThreads, POST_MIN_CTAS) fleet_post_kernel
     const double temp_ref = 25, k_temp = 6.93E-2;
     const double s_temp = exp(k_temp * (p.temperature - temp_ref) * ((temp_ref + 273.15) / (p.temperature + 273.15)));  // :72-73
 
-    // The first entry of a CTA is static (entry blockIdx.x), further ones come from a counter; thread 0 fetches the NEXT
-    // entry's list record and env4 while the current one is processed, so the two dependent round trips are hidden.
+    // A work item is one CHUNK of an entry's vehicles (post_cv = ceil(N / post_chunks) <= kT of them): the chunks of an env
+    // are independent (each vehicle has its own rainflow state) and may run in different CTAs at different times.  They
+    // all read the env's env4 record when they start; whichever finishes LAST (per-entry counter) writes it back.
+    // The first item of a CTA is static (item blockIdx.x), further ones come from a counter; thread 0 fetches the NEXT
+    // item's list record and env4 while the current one is processed, so the two dependent round trips are hidden.
+    const int chunks = p.post_chunks, cv = p.post_cv;
+    const int items = count * chunks;
     if (tid == 0) {
         s_w = blockIdx.x; s_deg = 0;
-        if (s_w < count) { s_ent = wl_fetch(p, s_w, n_front); s_ev = p.env4[s_ent.x]; }
+        if (s_w < items) { s_ent = wl_fetch(p, s_w / chunks, n_front); s_ev = p.env4[s_ent.x]; }
     }
     for (;;) {
         __syncthreads();
-        const int w = s_w;
-        if (w >= count) break;
+        const int item = s_w;
+        if (item >= items) break;
+        const int w = item / chunks, chunk = item - w * chunks;
         const int2 ent = s_ent;
         const int e = ent.x, wf = ent.y;
         const int4 ev = s_ev;                           // {t (already advanced), t_start, ep_count, k_done}
         const int k_now = ev.x - ev.y;                  // newest history sample (samples 0..k_now exist)
+        const int n = chunk * cv + tid;                 // this thread's vehicle
+        const bool mine = tid < cv && n < N;
         int w_next = 0;
         int2 ent_next = make_int2(0, 0);
         int4 ev_next = make_int4(0, 0, 0, 0);
         if (tid == 0) {
             w_next = atomicAdd(p.wl_count + 1, 1) + (int)gridDim.x;
-            if (w_next < count) { ent_next = wl_fetch(p, w_next, n_front); ev_next = p.env4[ent_next.x]; }
+            if (w_next < items) { ent_next = wl_fetch(p, w_next / chunks, n_front); ev_next = p.env4[ent_next.x]; }
         }
         PT_START();
         PT_COUNT(11, 1);
         if (p.rf_on && (wf & (WL_TRIGGER | WL_FLUSH))) {
             PT_COUNT(12, 1);
-            for (int n0 = 0; n0 < N; n0 += kPostThreads) {   // (all lanes of a warp go in together)
-                const int n = n0 + tid;
-                const double deg = rf_vehicle(p, e, n, n < N, ev.w, k_now, (wf & WL_TRIGGER) != 0, s_temp, sm_stack + tid,
-                                              sm_queue + tid, sm_pend + tid);
-                if (deg != 0) atomicAdd(&s_deg, deg);
-            }
-        } else if (wf & WL_TRIGGER) {                   // EmpiricalDegradation: the last two samples only
+            const double deg = rf_vehicle<kT>(p, e, n, mine, ev.w, k_now, (wf & WL_TRIGGER) != 0, s_temp, sm_stack + tid,
+                                              sm_queue + tid, sm_pend + tid);             // (all lanes of a warp go in together)
+            if (deg != 0) atomicAdd(&s_deg, deg);
+        } else if ((wf & WL_TRIGGER) && mine) {         // EmpiricalDegradation: the last two samples only
             const double* hbase = p.hist + (size_t)e * p.RN;
-            for (int n = tid; n < N; n += kPostThreads) {
-                const size_t ii = (size_t)e * N + n;
-                double deg = 0;
-                if (k_now >= 1) deg = empirical_eval(p.dt, p.evse, hbase[(size_t)((k_now - 1) & p.Rm) * N + n], hbase[(size_t)(k_now & p.Rm) * N + n]);
-                p.n_cycles[ii] = 0;
-                p.last_deg[ii] = deg;
-                p.soh[ii] = p.soh[ii] - deg;
-                if (deg != 0) atomicAdd(&s_deg, deg);
-            }
+            const size_t ii = (size_t)e * N + n;
+            double deg = 0;
+            if (k_now >= 1) deg = empirical_eval(p.dt, p.evse, hbase[(size_t)((k_now - 1) & p.Rm) * N + n], hbase[(size_t)(k_now & p.Rm) * N + n]);
+            p.n_cycles[ii] = 0;
+            p.last_deg[ii] = deg;
+            p.soh[ii] = p.soh[ii] - deg;
+            if (deg != 0) atomicAdd(&s_deg, deg);
         }
         __syncthreads();
         PT_MARK(8);
         if (tid == 0 && s_deg != 0)
             atomicAdd(p.stats + (size_t)(w % kStatStripes) * FLEET_S__COUNT + FLEET_S_DEGRADATION, s_deg);
-        if (wf & WL_RESET) { PT_COUNT(13, 1); post_reset_env<kNorm, kAux>(p, e, ev, tid, kPostThreads); PT_MARK(14); }
-        else if (tid == 0 && p.rf_on) p.env4[e] = make_int4(ev.x, ev.y, ev.z, k_now);   // samples up to k_now are consumed
+        // FleetEnv.reset of this chunk's vehicles, as the SubprocVecEnv worker calls it right after a done step
+        int t0 = 0;
+        if (wf & WL_RESET) {
+            PT_COUNT(13, 1);
+            t0 = p.next_start ? p.next_start[e] : draw_start(p.seed, p.start_lo, p.start_hi, p.env_id_offset + e, ev.z);
+            if (mine) reset_slot<kNorm, kAux>(p, e, n, t0, p.obs ? p.obs + (size_t)e * p.D : nullptr, !p.carry);
+            PT_MARK(14);
+        }
+        if (tid == 0) {
+            bool last = true;
+            if (chunks > 1) {
+                __threadfence();
+                last = atomicAdd(p.wl_chunks + w, 1) == chunks - 1;
+                if (last) p.wl_chunks[w] = 0;
+            }
+            if (last) {
+                if (wf & WL_RESET) {
+                    p.env4[e] = make_int4(t0, t0, ev.z + 1, 0);
+                    p.env_f64[(size_t)EF_EP_RETURN * p.E + e] = 0;
+                } else if (p.rf_on) {
+                    p.env4[e] = make_int4(ev.x, ev.y, ev.z, k_now);    // samples up to k_now are consumed
+                }
+            }
+        }
         __syncthreads();                                 // everybody has read s_w / s_ent / s_ev / s_deg
         PT_MARK(9);
         if (tid == 0) { s_w = w_next; s_ent = ent_next; s_ev = ev_next; s_deg = 0; }
@@ -2067,7 +2097,7 @@ struct FleetHandle {
     std::string err;
     size_t smem_step = 0, smem_post = 0, smem_pf = 0;
     int grid_pf = 0, use_pf = 0, pf_v = 1;   // pf_v: vehicles per compute thread of the pf kernel
-    int grid = 0, grid_post = 0, need_post = 0, num_sms = 0;
+    int grid = 0, grid_post = 0, need_post = 0, num_sms = 0, post_threads = kPostThreads;
     int max_smem_optin = 0;
     double* charge_log_buf = nullptr;   // fleet_enable_charge_log
     int host_zerocopy = 1;              // fleet_step_host: use page-locked host buffers in place (FLEETSTEP_HOST_ZEROCOPY)
@@ -2156,10 +2186,12 @@ StepKernel pick_pf_v(const FleetHandle* h, bool log) {
     return h->c.aux ? fleet_step_pf_kernel<false, true, false, kV> : fleet_step_pf_kernel<false, false, false, kV>;
 }
 StepKernel pick_pf(const FleetHandle* h, bool log) { return h->pf_v == 2 ? pick_pf_v<2>(h, log) : pick_pf_v<1>(h, log); }
-StepKernel pick_post(const FleetHandle* h) {
-    if (h->c.normalize) return h->c.aux ? fleet_post_kernel<true, true> : fleet_post_kernel<true, false>;
-    return h->c.aux ? fleet_post_kernel<false, true> : fleet_post_kernel<false, false>;
+template <int kT>
+StepKernel pick_post_t(const FleetHandle* h) {
+    if (h->c.normalize) return h->c.aux ? fleet_post_kernel<true, true, kT> : fleet_post_kernel<true, false, kT>;
+    return h->c.aux ? fleet_post_kernel<false, true, kT> : fleet_post_kernel<false, false, kT>;
 }
+StepKernel pick_post(const FleetHandle* h) { return h->post_threads == 32 ? pick_post_t<32>(h) : pick_post_t<64>(h); }
 StepKernel pick_reset(const FleetHandle* h) {
     if (h->c.normalize) return h->c.aux ? fleet_reset_kernel<true, true> : fleet_reset_kernel<true, false>;
     return h->c.aux ? fleet_reset_kernel<false, true> : fleet_reset_kernel<false, false>;
@@ -2623,12 +2655,18 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
     // per-batch reversal lists
     h->num_sms = prop.multiProcessorCount;
     h->need_post = (c.calc_degradation || c.auto_reset) ? 1 : 0;
-    h->smem_post = align16((size_t)(rfS + kRfQueue + 2 * kRfPend) * kPostThreads * 8);
+    // one warp per work item for fleets of up to 32 vehicles (cfg3: 35 instead of 49 us), two warps otherwise (a 50-vehicle
+    // env as two one-warp items of 25 lanes measured 55 against 52 us); FLEETSTEP_POST_THREADS=32|64 overrides
+    h->post_threads = env_int("FLEETSTEP_POST_THREADS", N <= 32 ? 32 : 64) == 32 ? 32 : 64;
+    p.post_chunks = (N + h->post_threads - 1) / h->post_threads;
+    p.post_cv = (N + p.post_chunks - 1) / p.post_chunks;
+    if (p.post_chunks > 1 && (rc = dev_alloc(h, &p.wl_chunks, (size_t)E))) return rc;
+    h->smem_post = align16((size_t)(rfS + kRfQueue + 2 * kRfPend) * h->post_threads * 8);
     if ((int64_t)h->smem_post > (int64_t)h->max_smem_optin) return fail(h, FLEET_E_INVALID, "rf_stack_depth does not fit the post kernel's shared memory");
     {
         int per_sm = 1;
         CUDA_TRY(h, cudaFuncSetAttribute(pick_post(h), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_post));
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post(h), kPostThreads, h->smem_post));
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pick_post(h), h->post_threads, h->smem_post));
         if (per_sm < 1) per_sm = 1;
         const int64_t g = (int64_t)h->num_sms * per_sm;
         h->grid_post = (int)(g < E ? g : E);
@@ -2656,16 +2694,16 @@ int fleet_create(const FleetConsts* consts, const FleetTables* tb, int32_t num_e
                 h->smem_pf = smpf;
                 const int ntiles = (E + pfB - 1) / pfB;
                 p.pf_B = pfB;
-                p.pf_bulk = ((pfB * h->D) % 4 == 0) ? 1 : 0;
+                p.pf_bulk = 1;                                  // (cleared per call when obs / terminal_obs are not 16-byte aligned)
                 p.pf_ntiles = ntiles;
                 p.pf_tile_hist = (unsigned int)((size_t)pfB * p.RN);
                 p.pf_pair = (N & 1) ? 0 : 1;
-                p.pf_obs2 = ((h->D & 1) == 0 && (Ha & 1) == 0) ? 1 : 0;
+                p.pf_obs2 = ((h->D & 1) == 0 && (Ha & 1) == 0 && (pfB * h->D) % 4 == 0) ? 1 : 0;
                 p.pf_cslots = pf_contrib_slots(pfB, N);
                 p.pf_cper = p.pf_pair ? N / 2 : N;
                 p.pf_envs_b = (int)align16((size_t)pfB * sizeof(PfEnv));
                 p.pf_contrib_b = (int)align16((size_t)kNQ * p.pf_cslots * 8);
-                p.pf_obs_b = (int)align16((size_t)pfB * h->D * 4);
+                p.pf_obs_b = (int)align16((size_t)pfB * h->D * 4 + 12);     // + the destination's phase inside a 16-byte line
                 p.pf_off_contrib = kPfEnvs * p.pf_envs_b;
                 p.pf_off_sums = p.pf_off_contrib + kPfOut * p.pf_contrib_b;
                 p.pf_off_obs = p.pf_off_sums + 2 * (int)align16((size_t)kNQ * pfB * 8);
@@ -2717,7 +2755,7 @@ int fleet_step(FleetHandle* h, const float* actions_dev, float* obs_dev, float* 
     h->launches++;
     if (tev) cudaEventRecord(tev[1], (cudaStream_t)stream);
     if (h->need_post) {   // daily degradation, then auto-reset, for the envs the step kernel put on the work list
-        pick_post(h)<<<h->grid_post, kPostThreads, h->smem_post, (cudaStream_t)stream>>>(p);
+        pick_post(h)<<<h->grid_post, h->post_threads, h->smem_post, (cudaStream_t)stream>>>(p);
         h->launches++;
     }
     if (tev) { cudaEventRecord(tev[2], (cudaStream_t)stream); h->tcount++; }

@@ -5,8 +5,8 @@ import numpy as np, torch
 import bench
 from fleetrl_b200._lib import FleetStepHandle, load_library
 
-class A: pass
-args = A(); args.use_case="lmd"; args.evs=50; args.episode_hours=24; args.carry=1; args.cfg=bench.CONFIGS["cfg2"]; args.raw_inputs=True; args.envs=65536
+sys.argv = [sys.argv[0], "--raw-inputs", "--config", os.environ.get("CONFIG", "cfg2")]
+args = bench.parse_args()
 built = bench.build_workload(args)
 E, N = args.envs, built.consts.num_evs
 dev = torch.device("cuda", 0)
@@ -27,7 +27,8 @@ for s in range(K):
     h.step_unchecked(ring[s % 8].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), term.data_ptr(), sp)
 L.fleet_debug_pf_clk(buf, 1)
 v = np.array(list(buf), dtype=np.float64)
-ntiles = (E + 4) // 5
+B = 256 // N
+ntiles = (E + B - 1) // B
 print("epilogue detail: any_reset %.0f | bulk store issue %.0f" % (v[7] / (K * ntiles), v[6] / (K * ntiles)))
 ep = v[:6] / (K * ntiles)
 print("epilogue warp, cycles per tile: pre-Done %.0f | wait Done %.0f | store+sums %.0f | wait_read %.0f | stage_env+arrive %.0f | finalise %.0f | total %.0f"
