@@ -130,8 +130,12 @@ enum {
     FLEET_F_LAST_DEG = 16,   /* double [E][N]  degradation returned by the last daily evaluation               */
     FLEET_F_OVERLOAD = 17,   /* double [E]     grid overload kW of the last step  load_calculation.py:93       */
     FLEET_F_SOC_VIOL = 18,   /* double [E]     cum_soc_missing of the last step   fleet_environment.py:544,661 */
-    FLEET_F_CHARGE_LOG = 19, /* double [E][N]  EvCharger's charge_log of the last step (kWh into (+) / out of (-) each battery),
-                              *                 ev_charger.py:212; only kept after fleet_enable_charge_log(h, 1)           */
+    FLEET_F_CHARGE_LOG = 19, /* double [E][N]  each vehicle's OWN energy of the last step (kWh into (+) / out of (-) its battery);
+                              *                 only kept after fleet_enable_charge_log(h, 1).  The reference's charge_log entry
+                              *                 (ev_charger.py:212) is charging_energy + discharging_energy, two locals that
+                              *                 survive from car to car (:81-82), so a car's entry also carries the last
+                              *                 opposite-sign car's energy: the log ring (fleet_enable_log) reproduces exactly
+                              *                 that column, this field keeps the physical per-vehicle quantity            */
     FLEET_F__COUNT = 20
 };
 
