@@ -1248,11 +1248,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     // the suspend-time hint (ns) only bounds how long the hardware may park the thread before it re-checks; the thread
     // resumes as soon as the phase completes, so a generous hint just means fewer spin iterations in the issue slots
     uint32_t ok;
+#ifndef MBAR_HINT_NS
+#define MBAR_HINT_NS 20000
+#endif
+#if MBAR_HINT_NS < 0      /* plain polling: test_wait never suspends */
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)MBAR_HINT_NS) : "memory");
+#endif
     return ok != 0;
 }
 // Epilogue-warp variant: the two epilogue warps wait most of a tile period; every failed try costs issue slots the compute
@@ -1279,17 +1290,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #define PF_STAT_ADD(ptr, v) atomicAdd(ptr, v)
 #endif
 #ifdef PF_TIMING
-__device__ unsigned long long g_pf_clk[16];
+__device__ unsigned long long g_pf_clk[16 + 128];   // [16]: per role; [16 + warp * 8 + mark]: per compute warp (PF_FLUSH_W)
 #define PF_MARK(k) do { const long long _c = clock64(); _acc[(k) & 7] += (unsigned long long)(_c - _pt); _pt = _c; } while (0)
 #define PF_START() long long _pt = clock64()
 #define PF_SETTLE() do { int _d; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(_d) : "r"((uint32_t)__cvta_generic_to_shared(smem_raw)) : "memory"); if (_d == 0x7fffffff) _acc[7]++; } while (0)
 #define PF_DECL() unsigned long long _acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define PF_FLUSH(base) do { if ((threadIdx.x & 31) == 0) { for (int _k = 0; _k < 8; _k++) if (_acc[_k]) atomicAdd(&g_pf_clk[(base) + _k], _acc[_k]); } } while (0)
+// timeline of CTA 0, iterations 16..23: g_pf_trace[role 0..9 (compute warps, epilogue 0, epilogue 1)][iteration][event]
+__device__ unsigned long long g_pf_trace[10 * 8 * 8];
+#define PF_TRACE(role_, it_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it_) >= 16 && (it_) < 24) g_pf_trace[((role_) * 8 + ((it_) - 16)) * 8 + (ev_)] = (unsigned long long)clock64(); } while (0)
+#define PF_FLUSH(base) do { if ((threadIdx.x & 31) == 0) { for (int _k = 0; _k < 8; _k++) if (_acc[_k]) { atomicAdd(&g_pf_clk[(base) + _k], _acc[_k]); if ((base) == 8) atomicAdd(&g_pf_clk[16 + (threadIdx.x >> 5) * 8 + _k], _acc[_k]); } } } while (0)
 #else
 #define PF_MARK(k) do {} while (0)
 #define PF_START() do {} while (0)
 #define PF_SETTLE() do {} while (0)
 #define PF_DECL() do {} while (0)
+#define PF_TRACE(role_, it_, ev_) do {} while (0)
 #define PF_FLUSH(base) do {} while (0)
 #endif
 #ifdef PF_SPEC_N
@@ -1381,6 +1396,7 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             mbar_wait_epi(&bar_done[buf], (uint32_t)((it / kPfOut) & 1));   // the compute warps have written tile `tile`
             PF_SETTLE();
             PF_MARK(1);
+            PF_TRACE(9, it, 0);
 
             // ---- observation tile -> HBM
             const bool use_bulk = p.pf_bulk && nb == B && !s_any_reset[it % kPfEnvs] && p.obs != nullptr;
@@ -1410,7 +1426,9 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             PF_MARK(6);
             // ---- per-env sums: one lane per (quantity, env); five interleaved partial sums in car order, combined in
             // a fixed order (deterministic run to run; the dependent-add chain is 5x shorter than a sequential sum)
+            PF_TRACE(9, it, 1);
             if (it >= 2) mbar_wait(&bar_sums_free[sbuf], (uint32_t)(((it >> 1) - 1) & 1));
+            PF_TRACE(9, it, 2);
 #ifdef PF_NOEPI
             if (lane < kNQ * nb) sums_w[lane] = 0;
             for (int w = lane; w < 0; w += 32) {
@@ -1428,11 +1446,13 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_sums_ready[sbuf]);
             PF_MARK(2);
+            PF_TRACE(9, it, 3);
             if (p.pf_bulk && (use_bulk ? lane == 0 : lane < nb)) bulk_store_wait_read();
             __syncwarp();
             PF_MARK(3);
             if (lane == 0) mbar_arrive(&bar_free[buf]);       // contribution + obs buffers of this tile are free again
             PF_MARK(4);
+            PF_TRACE(9, it, 4);
         }
         PF_FLUSH(0);
         bulk_store_wait_read();
@@ -1498,11 +1518,13 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             stage_env(tile + 3 * G, (it + 3) % kPfEnvs);
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_env[(it + 3) % kPfEnvs]);
+            PF_TRACE(8, it, 0);
             envA = envQ; load_rows(tile + 4 * G);             // in flight during this iteration
             load_env4(tile + 5 * G);
             double ep_prev = 0;                               // episode return so far (lane < nb), fetched ahead of its use
             if (lane < nb) ep_prev = p.env_f64[(size_t)EF_EP_RETURN * p.E + e0 + lane];
             mbar_wait_epi(&bar_sums_ready[sbuf], (uint32_t)((it >> 1) & 1));   // warp 1 has summed tile `tile`
+            PF_TRACE(8, it, 1);
 
             // ---- env-level finalisation: one lane per env
 #ifdef PF_NOEPI
@@ -1549,6 +1571,7 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_sums_free[sbuf]);
+            PF_TRACE(8, it, 2);
         }
         return;
     }
@@ -1594,15 +1617,19 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
                 cp_async4_hint(st + kPfStA32 + j * 4, p.actions + i, stream);
 #ifndef PF_NOSTATE
                 cp_async8_hint(st + kPfStSoc + j * 8, p.soc + i, stream);
+#ifndef PF_NOHL
                 cp_async4_hint(st + kPfStHl + j * 4, p.hl + i, stream);
+#endif
                 cp_async8_hint(st + kPfStSoh + j * 8, p.soh + i, stream);
 #endif
-#ifndef PF_NOHIST
+#if !defined(PF_NOHIST) && !defined(PF_NOSDEGR)
                 cp_async8_hint(st + kPfStSdeg + j * 8, hp, stream);
 #endif
 #ifndef PF_NOREC
                 cp_async16_hint(st + kPfStR0 + j * 16, rp, keep);
+#ifndef PF_NOR1
                 cp_async16_hint(st + kPfStR1 + j * 16, rp + 1, keep);
+#endif
                 if (n < H) cp_async4_hint(st + kPfStHv + j * 4, hd, keep);
 #endif
             } else {                                          // two vehicles: every copy twice as wide (j, n, i are even)
@@ -1650,12 +1677,19 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
         cp_async_wait_group<kPfStages - 1>();
         const unsigned char* stp = smem_raw + p.pf_off_stage + stg * kPfStageBytes;
         PF_MARK(4);
+        PF_TRACE(tid >> 5, it, 0);
         mbar_wait(&bar_env[ebuf], ph_env);                    // env scratch of this tile is staged
         PF_SETTLE();
         PF_MARK(0);
+        PF_TRACE(tid >> 5, it, 1);
         if (it >= kPfOut) mbar_wait(&bar_free[buf], ph_free);  // contribution + obs buffers are free again
         PF_SETTLE();
         PF_MARK(2);
+        PF_TRACE(tid >> 5, it, 2);
+#ifdef PF_TIMING_LDS      /* one more shared-memory load round trip, timed on its own */
+        PF_SETTLE();
+        PF_MARK(7);
+#endif
 
         double q_rew = 0, q_cash = 0, q_ath = 0, q_miss = 0, q_nviol = 0;   // these vehicles' terms of the per-env sums
         double o_soc[kV], o_sdeg[kV], o_en[kV];                             // new state, stored after the hand-off
@@ -1771,6 +1805,7 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (bulk store)
         mbar_arrive(&bar_done[buf]);
         PF_MARK(5);
+        PF_TRACE(tid >> 5, it, 3);
         // the new state goes to HBM after the hand-off: the fence above (MEMBAR + proxy fence) then only has shared-memory
         // stores to wait for, not these
 #ifdef PF_NOSTG
@@ -1791,7 +1826,9 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
             } else {
 #ifndef PF_NOSTATE
                 __stcs(p.soc + i, o_soc[0]);
+#ifndef PF_NOHL
                 __stcs(p.hl + i, o_hl[0]);
+#endif
 #endif
 #ifndef PF_NOHIST
                 __stcs(p.hist + o_hist, o_sdeg[0]);
@@ -1802,6 +1839,7 @@ __global__ void __launch_bounds__(pf_threads(kV)) __maxnreg__(pf_maxreg(kV)) fle
         PF_MARK(6);
         issue_copies(tile + kPfStages * G, ev_next, stg);     // refill the stage this tile has just consumed
         PF_MARK(3);
+        PF_TRACE(tid >> 5, it, 4);
         if (++stg == kPfStages) stg = 0;
         if (++ebuf == kPfEnvs) { ebuf = 0; ph_env ^= 1u; }
         if (++buf == kPfOut) { buf = 0; if (it >= kPfOut) ph_free ^= 1u; }
@@ -2415,8 +2453,13 @@ int32_t fleet_debug_post_clk(unsigned long long* out, int32_t reset) {
 #ifdef PF_TIMING
 int32_t fleet_debug_pf_clk(unsigned long long* out, int32_t reset) {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, g_pf_clk, sizeof(unsigned long long) * 16);
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_pf_clk, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(out, g_pf_clk, sizeof(unsigned long long) * (16 + 128));     /* out: 144 values */
+    if (reset) { unsigned long long z[16 + 128] = {0}; cudaMemcpyToSymbol(g_pf_clk, z, sizeof(z)); }
+    return 0;
+}
+int32_t fleet_debug_pf_trace(unsigned long long* out) {   /* out: 640 values, g_pf_trace of the last launch */
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_pf_trace, sizeof(unsigned long long) * 640);
     return 0;
 }
 #endif
