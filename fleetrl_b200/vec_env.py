@@ -101,6 +101,9 @@ class FleetVecEnv(_VecEnvBase):
         self._actions = None
         self.render_mode = None
         self._start_override = None
+        # env_config["log_data"]=True (the reference's evaluation runs use one env): log the first envs (at most 8)
+        if self.built.rc is not None and self.built.rc.cfg.get("log_data", False):
+            self.enable_log(indices=list(range(min(E, 8))))
         if output == "numpy":
             self._h_act = torch.zeros((E, self.num_cars), dtype=torch.float32).pin_memory()
             self._h_obs = torch.zeros((E, D), dtype=torch.float32).pin_memory()
@@ -189,23 +192,7 @@ class FleetVecEnv(_VecEnvBase):
 
     def _log_frames(self):
         """DataLogger.log as one DataFrame per logged env (columns LOG_COLUMNS)."""
-        L = int(self.built.consts.episode_steps)
-        frames = {}
-        for rec in self.handle.read_log():
-            first = rec["rows_total"] - len(rec["kind"])          # rows that fell out of the ring
-            rows = []
-            for r in range(len(rec["kind"])):
-                kind = int(rec["kind"][r])
-                rows.append({"Episode": (first + r) // L + 1,                                  # data_logger.py:51
-                             "Time": pd.Timestamp(self.built.dates[int(rec["time_idx"][r])]),
-                             "Observation": rec["obs"][r], "Action": rec["action"][r],
-                             "Reward": float(rec["reward"][r]), "Cashflow": float(rec["cashflow"][r]),
-                             "Penalties": float(rec["penalties"][r]), "Grid overloading": float(rec["overload"][r]),
-                             "SOC violation": float(rec["soc_viol"][r]),
-                             "Degradation": rec["degradation"][r] if kind == 2 else 0.0,
-                             "Charging energy": rec["charging_energy"][r], "SOH": rec["soh"][r]})
-            frames[rec["env"]] = pd.DataFrame(rows, columns=list(self.LOG_COLUMNS))
-        return frames
+        return {rec["env"]: _log_frame(rec, self.built) for rec in self.handle.read_log()}
 
     def baseline_actions(self, policy, out=None):
         """Actions [E, N] (float32, on the device) of one of the reference's rule-based benchmark policies at every env's
@@ -322,6 +309,27 @@ class FleetVecEnv(_VecEnvBase):
         return t.cpu().numpy() if self.output == "numpy" else t
 
 
+LOG_COLUMNS = FleetVecEnv.LOG_COLUMNS
+
+
+def _log_frame(rec, built):
+    """One env's rows of the device-side log ring (FleetStepHandle.read_log) as the reference's DataLogger frame."""
+    L = int(built.consts.episode_steps)
+    first = rec["rows_total"] - len(rec["kind"])          # rows that fell out of the ring
+    rows = []
+    for r in range(len(rec["kind"])):
+        kind = int(rec["kind"][r])
+        rows.append({"Episode": (first + r) // L + 1,                                  # data_logger.py:51
+                     "Time": pd.Timestamp(built.dates[int(rec["time_idx"][r])]),
+                     "Observation": rec["obs"][r], "Action": rec["action"][r],
+                     "Reward": float(rec["reward"][r]), "Cashflow": float(rec["cashflow"][r]),
+                     "Penalties": float(rec["penalties"][r]), "Grid overloading": float(rec["overload"][r]),
+                     "SOC violation": float(rec["soc_viol"][r]),
+                     "Degradation": rec["degradation"][r] if kind == 2 else 0.0,
+                     "Charging energy": rec["charging_energy"][r], "SOH": rec["soh"][r]})
+    return pd.DataFrame(rows, columns=list(LOG_COLUMNS))
+
+
 class FleetEnv:
     """Drop-in for the reference's gym.Env: ONE environment, NumPy in / NumPy out, no auto-reset.
 
@@ -330,11 +338,16 @@ class FleetEnv:
 
     metadata = {"render_modes": []}
 
-    def __init__(self, env_config, inputs: FleetInputs = None, device=0):
+    def __init__(self, env_config, inputs: FleetInputs = None, device=0, log_rows=None):
         self.built = build_fleet(env_config, inputs, auto_reset=False, carry_degradation_state=True)
         c = self.built.consts
         self.num_cars = int(c.num_evs)
         self.handle = FleetStepHandle(c, self.built.tables, 1, device=device)
+        # env_config["log_data"] (fleet_environment.py:129,420,679): keep the DataLogger rows on the device (ring of
+        # log_rows rows, default four episodes) and hand them out as the reference's frame in get_log()
+        self.log_data = bool(self.built.rc.cfg.get("log_data", False)) if self.built.rc is not None else False
+        if self.log_data:
+            self.handle.enable_log([0], int(log_rows) if log_rows else 4 * int(c.episode_steps))
         dev = self.handle.device
         self.observation_space = observation_box(self.handle.D, bool(c.normalize))
         self.action_space = action_box(self.num_cars)
@@ -387,4 +400,7 @@ class FleetEnv:
         return None
 
     def get_log(self):
-        return pd.DataFrame([self.handle.stats()])
+        """DataLogger.log (data_logger.py:55-68) when the env was built with log_data=True, else the reduced statistics."""
+        if not self.log_data:
+            return pd.DataFrame([self.handle.stats()])
+        return _log_frame(self.handle.read_log()[0], self.built)

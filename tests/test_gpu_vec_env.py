@@ -67,6 +67,31 @@ def test_vec_env_matches_oracle(output):
     env.close()
 
 
+def FleetVecEnv_LOG_COLUMNS():
+    from fleetrl_b200 import FleetVecEnv
+    return FleetVecEnv.LOG_COLUMNS
+
+
+def test_fleet_env_log_data_flag():
+    """env_config["log_data"]=True (fleet_environment.py:129): FleetEnv.get_log() is the DataLogger frame — one reset row and
+    one row per step that does not end the episode (:420-432, :679-690)."""
+    from fleetrl_b200 import FleetEnv
+    cfg = default_config("lmd", time_picker="static", episode_length=24, log_data=True)
+    env = FleetEnv(cfg, inputs=_inputs("lmd", 3))
+    env.reset()
+    rng = np.random.default_rng(3)
+    rewards = []
+    for s in range(96):
+        _, r, done, _, _ = env.step(rng.uniform(-1, 1, 3).astype(np.float32))
+        rewards.append(r)
+    assert done
+    log = env.get_log()
+    assert list(log.columns) == list(FleetVecEnv_LOG_COLUMNS()) and len(log) == 96      # reset row + 95 non-finishing steps
+    np.testing.assert_allclose(log["Reward"].to_numpy(dtype=float)[1:], rewards[:-1], rtol=1e-12, atol=1e-12)
+    assert (log["Episode"] == 1).all() and log["Time"].iloc[1] - log["Time"].iloc[0] == pd.Timedelta(minutes=15)
+    env.close()
+
+
 def test_fleet_env_gym_api():
     from fleetrl_b200 import FleetEnv
     cfg = default_config("ct", time_picker="static", episode_length=48)
@@ -89,6 +114,7 @@ def test_fleet_env_gym_api():
         np.testing.assert_allclose(r, o_r[0], rtol=1e-11, atol=1e-10)
         assert done == bool(o_d[0])
     assert done and env.is_done()
+    assert list(env.get_log().columns) != list(FleetVecEnv_LOG_COLUMNS())          # log_data=False: reduced statistics
     with pytest.raises(TypeError):
         env.step(np.array([np.nan, 0, 0, 0], dtype=np.float32))
     env.close()
