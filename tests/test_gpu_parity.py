@@ -44,7 +44,11 @@ KERNELS = ([(n, "pf") for n in sorted(CASES) if CASES[n]["n_evs"] >= 8 and CASES
            + [(n, "generic") for n in sorted(CASES)]
            + [(n, "pf+ring4+stack2") for n in ("lmd_50ev", "ct_20ev_two_trips", "lmd_9ev_norm_nocarry")]
            + [(n, "generic+ring8+stack3") for n in ("lmd_300ev", "lmd_7ev", "lmd_1ev", "lmd_5ev_soh09", "lmd_4ev_no_autoreset")]
-           + [("lmd_9ev_10day_episodes", "pf+ring16+stack4"), ("lmd_50ev", "pf+ring128+stack64")])
+           + [("lmd_9ev_10day_episodes", "pf+ring16+stack4"), ("lmd_50ev", "pf+ring128+stack64")]
+           # the two-vehicles-per-thread variant of the pf kernel (off by default, FLEETSTEP_PF_V=2) and the two-warp /
+           # one-warp work items of the post kernel
+           + [("lmd_50ev", "pf+v2"), ("ct_20ev_two_trips", "pf+v2+post64"), ("ut_10ev_e50", "pf+v2"), ("lmd_50ev_e36", "pf+post32"),
+              ("lmd_300ev", "generic+post32")])
 
 
 @pytest.mark.parametrize("name,kernel", KERNELS)
@@ -55,7 +59,8 @@ def test_gpu_vs_oracle(name, kernel, monkeypatch):
         monkeypatch.setenv("FLEETSTEP_RF_EXT_SLOTS", "40000")      # tiny inline stacks: every vehicle may need an extension slot
     else:
         monkeypatch.delenv("FLEETSTEP_RF_EXT_SLOTS", raising=False)
-    for var, key in (("FLEETSTEP_RF_RING", "ring"), ("FLEETSTEP_RF_STACK", "stack"), ("FLEETSTEP_RF_EXT", "ext")):
+    for var, key in (("FLEETSTEP_RF_RING", "ring"), ("FLEETSTEP_RF_STACK", "stack"), ("FLEETSTEP_RF_EXT", "ext"),
+                     ("FLEETSTEP_PF_V", "v"), ("FLEETSTEP_POST_THREADS", "post")):
         val = [t[len(key):] for t in kernel.split("+")[1:] if t.startswith(key)]
         if val:
             monkeypatch.setenv(var, val[0])
