@@ -75,8 +75,11 @@ def parse_args():
                          "uncontrolled_charging.py:51-54; exercises the overload / overcharging penalty paths, SURVEY 8d cfg2)")
     ap.add_argument("--raw-inputs", action="store_true",
                     help="skip the CSV text round trip of the synthetic inputs (saves ~8 s of start-up; diagnostic runs)")
-    ap.add_argument("--settle-episodes", type=int, default=0,
-                    help="extra untimed episodes after de-phasing (rainflow_length converges to its running maximum)")
+    ap.add_argument("--settle-episodes", type=int, default=10,
+                    help="extra untimed episodes after de-phasing: an env object lives for the whole training run, and its "
+                         "RainflowSeiDegradation.rainflow_length (carried across episodes, rainflow_sei_degradation.py:195) converges "
+                         "to its running maximum within a few episodes, after which fewer cycles need a stress evaluation; "
+                         "without settling a 20-step window runs 5 %% slower than a 960-step one, with it 1.7 %%")
     args = ap.parse_args()
     cf = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -259,7 +262,8 @@ def workload_config(args, built, D):
             "episode_steps": int(built.consts.episode_steps), "auto_reset": True,
             "carry_degradation_state": bool(args.carry), "actions": getattr(args, "actions", "random"),
             "episode_phase": "de-phased: env e is (e mod episode_steps) steps into its episode when timing starts, so "
-                             "every step sees ~E/episode_steps auto-resets and ~E/96 daily evaluations (SB3 steady state)",
+                             "every step sees ~E/episode_steps auto-resets and ~E/96 daily evaluations (SB3 steady state); "
+                             f"{getattr(args, 'settle_episodes', 0)} untimed episodes per env before timing (rainflow_length settled)",
             "l2_policy": "per-step working set (actions+state+obs ≈ 0.27 GB at cfg2) exceeds the 126 MB L2; "
                          "action tensors rotate through a ring"}
 
