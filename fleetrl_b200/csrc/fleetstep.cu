@@ -1,23 +1,30 @@
 // fleetstep.cu — B200 (sm_100a) implementation of the FleetRL environment step behind include/fleetstep.h.
 //
-// One fused kernel per call:
-//   fleet_step_kernel   EvCharger.charge + LoadCalculation.check_violation + ScoreConfig penalties + time advance +
-//                       departure/arrival logic + Observer/Normalization observation assembly + (at the daily 14:45
-//                       trigger) rainflow/SEI or linear degradation + SB3-style auto-reset, for E envs x N EVs.
-//   fleet_reset_kernel  FleetEnv.reset for the masked envs.
+// Two launches per fleet_step call, on the caller's stream:
+//   step kernel   fleet_step_pf_kernel (persistent, warp-specialised, software-pipelined; auto-reset on, 8 <= N <= 256) or
+//                 fleet_step_kernel (generic: any N, frozen envs): EvCharger.charge + LoadCalculation.check_violation +
+//                 ScoreConfig penalties + time advance + departure/arrival logic + Observer/Normalization observation
+//                 assembly for E envs x N EVs; appends the new soc_deg sample to a small per-env ring and pushes envs that
+//                 need more onto a device work list.
+//   post kernel   fleet_post_kernel: incremental rainflow (persistent three-point stack per vehicle) over the ring samples,
+//                 at the daily 14:45 trigger RainflowSeiDegradation / EmpiricalDegradation.calculate_degradation, then the
+//                 SB3-style auto-reset of finished envs.
+//   fleet_reset_kernel  FleetEnv.reset for the masked envs; policy_kernel (rule-based baselines), fleet_log_kernel
+//                 (DataLogger rows of selected envs), small gather / scatter / statistics kernels.
 // Reference: fleetrl/fleet_env/fleet_environment.py:330-702, utils/ev_charging/ev_charger.py:39-231,
 // utils/load_calculation/load_calculation.py:83-94, fleet_env/config/score_config.py:26-41,
 // utils/observation/observer_bl_pv.py:12-136, utils/normalization/*.py,
-// utils/battery_degradation/rainflow_sei_degradation.py:91-212, empirical_degradation.py:29-99.
+// utils/battery_degradation/rainflow_sei_degradation.py:91-212, empirical_degradation.py:29-99, rainflow 3.2.0.
 //
-// Mapping: a CTA owns a tile of B = floor(256/N) consecutive envs; thread j of the tile owns the
+// Mapping: a CTA works on tiles of B = floor(256/N) consecutive envs; thread j of the tile owns the
 // (env, EV) pair ("slot") j = b*N + n.  All [E][N] state is env-major, so slot j of the tile touches element
 // e0*N + j of every array: perfectly coalesced scalar loads/stores with no padding.  Per-env reductions over the
-// EVs go through shared memory and are summed SEQUENTIALLY IN CAR ORDER by one thread per (env, quantity), which
-// reproduces the reference's Python accumulation order bit for bit.  Everything that depends only on the time
-// index (price/tariff factors, PV share, grid margin, the observation header with its look-ahead windows and
-// calendar features) is precomputed once on the host in float64 with the reference's operation order and staged in
-// HBM (L2-resident, ~35 MB at N=50,T=35040); the kernel gathers it by time index.
+// EVs go through shared memory and are summed in a FIXED order by one lane per (env, quantity) (deterministic run to
+// run; a documented re-association of the reference's Python accumulation).  Everything that depends only
+// on the time index (price/tariff factors, PV share, grid margin, the observation header with its look-ahead windows and
+// calendar features, the per-(time, EV) schedule record with its auxiliary observation terms) is precomputed once on the
+// host in float64 with the reference's operation order and staged in HBM (~64 MB at N=50, T=35040); the kernels gather
+// it by time index.
 //
 // Arithmetic: float64 with -fmad=false (no FMA contraction), operation order of the reference; float32 only where
 // the reference casts (observation, reward output) and for hours_left, whose values are exact multiples of dt
