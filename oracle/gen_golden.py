@@ -289,6 +289,14 @@ CASES = [
     # CSV dialects (schedule.write_reference_csvs) and read back by the unmodified reference
     dict(name="cfg2_lmd_50ev_gen", cfg_over=dict(TARIFF, price_name=None, tariff_name=None), starts=["2020-03-10 06:15"],
          n_steps_per_ep=96, action_fn=uniform, n_evs=50, seed=11, generated=101),
+    # SURVEY 8d cfg2 parity subset: sixteen 96-step episodes at the cfg2 fleet shape (every weekday and time of day, three weeks), on ONE env object
+    # (degradation state carried from episode to episode like in an SB3 worker)
+    dict(name="cfg2_lmd_50ev_gen_16ep", cfg_over=dict(TARIFF, price_name=None, tariff_name=None),
+         starts=["2020-03-02 00:00", "2020-03-03 05:30", "2020-03-04 11:15", "2020-03-05 17:45", "2020-03-06 23:00",
+                 "2020-03-08 08:15", "2020-03-09 14:00", "2020-03-10 20:30", "2020-03-12 02:45", "2020-03-13 09:00",
+                 "2020-03-14 15:15", "2020-03-15 21:30", "2020-03-17 03:45", "2020-03-18 10:00", "2020-03-19 16:15",
+                 "2020-03-20 22:30"],
+         n_steps_per_ep=96, action_fn=mixed_pm, n_evs=50, seed=15, generated=101),
     dict(name="cfg3_ct_20ev_48h_gen", cfg_over=dict(TARIFF, use_case="ct", episode_length=48, price_name=None, tariff_name=None),
          starts=["2020-06-08 05:00"], n_steps_per_ep=192, action_fn=uniform, n_evs=20, seed=12, generated=102),
     dict(name="cfg4_ut_50ev_1h_priceonly_gen",
